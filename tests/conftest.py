@@ -1,0 +1,67 @@
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+class Golden:
+    """A tests/golden/<name>.npz case written by make_golden.py (outputs of the
+    reference's own code); frames are regenerated from their seeds and checked
+    against the stored sha256."""
+
+    def __init__(self, name):
+        self.z = np.load(os.path.join(GOLDEN, name + '.npz'))
+        self.meta = json.loads(str(self.z['meta']))
+        b = self.z['boxes']
+        self.boxes = [((int(r[0]), int(r[1]), int(r[2]), int(r[3])), int(r[4])) for r in b]
+        self.shapes = [(r[0][3], r[0][2]) for r in self.boxes]
+        self._frames = {}
+
+    def frame(self, fi):
+        from vi_b200 import synth
+        if fi not in self._frames:
+            m = self.meta
+            fr = synth.make_frame(m['seeds'][fi], [r for r, _ in self.boxes], H=m['H'], W=m['W'], **m['synth_kw'])
+            assert hashlib.sha256(fr.tobytes()).hexdigest() == m['frame_sha256'][fi], 'synthetic generator drifted'
+            self._frames[fi] = fr
+        return self._frames[fi]
+
+    def masks(self, key):
+        """Unpack a bit-packed mask list -> list of uint8 0/255 arrays."""
+        blob = self.z[key]
+        out, off = [], 0
+        for (h, w) in self.shapes:
+            nb = (h * w + 7) // 8
+            bits = np.unpackbits(blob[off:off + nb])[:h * w].reshape(h, w)
+            out.append((bits * 255).astype(np.uint8))
+            off += nb
+        assert off == len(blob)
+        return out
+
+    def defects(self, fi, r):
+        present = self.z[f'f{fi}_r{r}_def_present']
+        ms = self.masks(f'f{fi}_r{r}_def')
+        return [m if p else None for m, p in zip(ms, present)]
+
+
+@pytest.fixture(scope='session')
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+    return get
