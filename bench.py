@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (BASELINE.json metric: units/s on synthetic
+4096x3000 mold images with the reference's grid.json grid).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the full per-unit inspection path (segmentation +
+defect pass + verdict) over one batch of `--images` (default 64 = configs[1])
+synthetic frames per GPU.  `value` is measured with the frames already resident
+in HBM; `e2e` goes through the host-buffer C-ABI call (pinned host frames in,
+masks + records out, copies inside the timed region).  Multi-GPU: one process
+per GPU (torchrun), images sharded by rank, one NCCL all-gather of the per-unit
+record table per step; weak scaling.
+
+`--impl reference` times the reference's own CPU path (the cv2 oracle port,
+oracle/ref_cv2.py -- the reference itself needs PyQt6 and is absent on the GPU
+box) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+GRID_BASE = (251, 232, 316, 315)          # the reference's grid.json: 2 blocks x (4 x 6) units of 316x315
+GRID_ARGS = (4, 6, 2, 1, 133, 136, 252, 0)
+W, H = 4096, 3000
+UNIT_PX = 316 * 315
+ALGO_BYTES_PER_PX = 3                      # 1 B gray in + 1 B seg mask out + 1 B defect mask out
+
+
+def grid_boxes():
+    from vi_b200.grid import generate_grid
+    return generate_grid(GRID_BASE, *GRID_ARGS)
+
+
+# --------------------------------------------------------------------------- CPU arm
+_CPU_FRAMES = None
+
+
+def _cpu_init():
+    import cv2
+    cv2.setNumThreads(1)
+
+
+def _cpu_one(i):
+    from oracle import ref_cv2 as R
+    recs, _, _ = R.inspect_frame(_CPU_FRAMES[i], grid_boxes(), R.Params(), (), None, True)
+    return sum(1 for r in recs if r['status'] == R.STATUS_NG)
+
+
+def cpu_reference_run(frames, cores):
+    """Units/s of the reference CPU path on `cores` processes (images sharded)."""
+    import multiprocessing as mp
+    global _CPU_FRAMES
+    _CPU_FRAMES = frames
+    n_units = len(grid_boxes())
+    if cores <= 1:
+        _cpu_init()
+        t0 = time.perf_counter()
+        ng = [_cpu_one(i) for i in range(len(frames))]
+        dt = time.perf_counter() - t0
+    else:
+        ctx = mp.get_context('fork')
+        with ctx.Pool(cores, initializer=_cpu_init) as pool:
+            pool.map(_cpu_one, range(min(cores, len(frames))))      # warm the workers (imports, page-in)
+            t0 = time.perf_counter()
+            ng = pool.map(_cpu_one, range(len(frames)), chunksize=1)
+            dt = time.perf_counter() - t0
+    return len(frames) * n_units / dt, dt, int(sum(ng))
+
+
+def make_frames(seeds):
+    from vi_b200 import synth
+    boxes = [b for b, _ in grid_boxes()]
+    return [synth.make_frame(s, boxes, H=H, W=W) for s in seeds]
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, ln in self.lines:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in ln.split(',')]
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- main arms
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_frames = max(cores, 8) if args.ref_frames <= 0 else args.ref_frames
+    n_frames = min(n_frames, 2 * cores)
+    frames = make_frames(range(n_frames))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_run(frames[:min(len(frames), cores)], cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt, ng = cpu_reference_run(frames, cores)
+        vals.append(v); t_all += dt
+    value = float(np.mean(vals))
+    sample = f"{n_frames} frames x 48 units per step ({n_frames * 48} units), {cores} processes x 1 cv2 thread"
+    out = {
+        "impl": "reference", "metric": "units/s", "value": value, "unit": "units/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: 4096x3000 frames, grid.json grid (48 units of 316x315), defaults "
+                               "(otsu, blur 3, morph 3, thr 24, min-area 20, erode 6); bounded sample", "images_per_step": n_frames},
+        "gpix_per_s": value * UNIT_PX / 1e9,
+        "cpu_baseline": {"value": value, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import vi_b200
+    from vi_b200.grid import Grid
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    boxes = grid_boxes()
+    n_units = len(boxes)
+    n_img = args.images
+    insp = vi_b200.Inspector(local_rank)
+    insp.configure(Grid(boxes=boxes), is_reference=True)
+    params = vi_b200.default_params()
+
+    # synthetic frames: `--distinct` distinct seeds per rank, tiled to n_img (pinned host + device copies)
+    n_dist = min(args.distinct, n_img)
+    seeds = [rank * n_img + i for i in range(n_dist)]
+    uniq = make_frames(seeds)
+    h_frames_t = torch.empty((n_img, H, W), dtype=torch.uint8, pin_memory=True)
+    h_frames = h_frames_t.numpy()
+    for i in range(n_img):
+        h_frames[i] = uniq[i % n_dist]
+    d_frames = h_frames_t.to(dev, non_blocking=True)
+    total_px = n_img * insp.unit_pixels
+    d_seg = torch.empty(total_px, dtype=torch.uint8, device=dev)
+    d_def = torch.empty(total_px, dtype=torch.uint8, device=dev)
+    d_rec = torch.empty((n_img * n_units, 64), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(d_rec) for _ in range(world)] if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step():
+        insp.inspect_batch(d_frames, params, seg_masks=d_seg, defect_masks=d_def, records=d_rec)
+        if world > 1:
+            dist.all_gather(gathered, d_rec)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = ms / args.steps
+    units_per_step = n_img * n_units * world
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # parity spot check of the timed outputs against the CPU oracle (first distinct frame of rank 0)
+    rec = d_rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    ng_gpu = int((rec['status'] == vi_b200.STATUS_NG).sum())
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    h_seg = torch.empty(total_px, dtype=torch.uint8, pin_memory=True).numpy()
+    h_def = torch.empty(total_px, dtype=torch.uint8, pin_memory=True).numpy()
+    h_rec = torch.empty(n_img * n_units * 64, dtype=torch.uint8, pin_memory=True).numpy().view(vi_b200.RECORD_DTYPE)
+    for _ in range(max(1, args.warmup // 2)):
+        insp.inspect_batch_host(h_frames, params, out=(h_rec, h_seg, h_def))
+    barrier()
+    e2e_steps = max(1, args.steps)
+    t0e = time.perf_counter()
+    for _ in range(e2e_steps):
+        insp.inspect_batch_host(h_frames, params, out=(h_rec, h_seg, h_def))
+        if world > 1:
+            dist.all_gather(gathered, torch.from_numpy(h_rec.view(np.uint8).reshape(-1, 64)).to(dev))
+    barrier()
+    e2e_s = (time.perf_counter() - t0e) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = units_per_step / e2e_s
+    assert np.array_equal(h_rec['status'], rec['status']), "host-buffer path and device-resident path disagree"
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak = 6650.0; peak_src = "fallback 6650 GB/s (of fallback)"
+        algo_bytes_per_launch = ALGO_BYTES_PER_PX * n_img * insp.unit_pixels
+        achieved = algo_bytes_per_launch / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step per rank
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        # CPU baseline: bounded sample on rank 0's host cores (N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_s = min(max(cores, 4), n_dist, 2 * cores)
+            v, dt, ng_cpu = cpu_reference_run(uniq[:n_s], cores)
+            ng_gpu_s = int((rec['status'][:n_s * n_units] == vi_b200.STATUS_NG).sum())
+            assert ng_cpu == ng_gpu_s, f"NG count differs: cpu {ng_cpu} vs gpu {ng_gpu_s}"
+            cpu = {"value": v, "unit": "units/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_s} of the same frames x 48 units ({n_s * n_units} units, {dt:.1f} s), "
+                             f"{cores} processes x 1 cv2 thread, oracle/ref_cv2.py; NG count equals the GPU's ({ng_cpu})"}
+        out = {
+            "metric": "units/s", "value": value, "unit": "units/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch of %d synthetic 4096x3000 frames per GPU, grid.json grid (48 units of "
+                                   "316x315), defaults (otsu, blur 3, morph 3, thr 24, min-area 20, erode 6)" % n_img,
+                       "images_per_gpu": n_img, "units_per_step": units_per_step, "distinct_frames_per_gpu": n_dist,
+                       "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2" % (n_img * H * W / 1e6),
+                       "collective": "all_gather of the 64 B/unit record table per step" if world > 1 else "none"},
+            "gpix_per_s": value * UNIT_PX / 1e9,
+            "frame_gpix_per_s": value / n_units * W * H / 1e9,
+            "ng_units": ng_gpu,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes_per_launch, "kernel": "vi_unit_kernel"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "units/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(n_img * H * W),
+                    "d2h_bytes_per_step": int(2 * total_px + n_img * n_units * 64)},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=64, help="frames per GPU per step (configs[1] = 64)")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic frames per GPU (tiled to --images)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the reference arm (0 = host cores)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+/*
+ * vi_b200.h -- C ABI of the B200 batch-inspection path.
+ *
+ * The reference (hazernest/Vision-Inspection-system-Segmentation-using-
+ * classical-computer-vision-) has no FFI layer: its seam is the Python module
+ * API of segmentation.py plus the compute body of one UI method.  Each entry
+ * point below cites the reference interface it replaces (file:line under the
+ * reference tree).  The Python host side (vi_b200.segmentation / vi_b200.api)
+ * binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: C linkage, plain pointers and sizes, no C++ / torch types.
+ * Every function returns 0 on success or a negative VI_ERR_* code;
+ * vi_last_error() returns a thread-local message for the last failure.
+ * There is no CPU fallback: every compute entry point runs CUDA kernels on the
+ * context's device and fails with VI_ERR_CUDA if it cannot.
+ *
+ * Threading: one vi_ctx per host thread and device.  vi_inspect_batch is
+ * asynchronous with respect to `stream`; all *_host / compat entry points
+ * block until their results are in the caller's host buffers.
+ */
+#ifndef VI_B200_H
+#define VI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VI_OK 0
+#define VI_ERR_ARG (-1)         /* bad argument (null pointer, rect outside frame, bad size) */
+#define VI_ERR_CUDA (-2)        /* CUDA runtime / launch failure                              */
+#define VI_ERR_UNSUPPORTED (-3) /* valid reference option not built yet (adaptive, canny)    */
+#define VI_ERR_TOO_LARGE (-4)   /* unit does not fit the shared-memory-resident path          */
+
+/* vi_unit_record.status */
+#define VI_STATUS_OK 0        /* detector returned None or area < min_area (indexing_ui.py:1687, :1699) */
+#define VI_STATUS_NG 1        /* defect area >= min_area (indexing_ui.py:1618, :1699)                   */
+#define VI_STATUS_ROI_EMPTY 2 /* ROI empty after erosion -> detector returns None (:1514-1516)          */
+
+typedef struct vi_ctx vi_ctx;
+
+/* Exclusion in base-unit-local pixels (indexing_ui.py:1811, :1816):
+ * shape 0 = rect (a,b,c,d) = (x,y,w,h); shape 1 = circle (a,b,c) = (cx,cy,r). */
+typedef struct vi_excl {
+    int32_t shape, a, b, c, d;
+} vi_excl;
+
+/* The reference's widget values (indexing_ui.py:799-806, 870-875, 1522, 1548). */
+typedef struct vi_params {
+    int32_t seg_method;    /* 0 otsu (default; unknown strings fall back to it, segmentation.py:87-89), 1 adaptive */
+    int32_t gaussian_blur; /* 3;  0 skips, even k -> k+1 (segmentation.py:78-79)          */
+    int32_t morph_kernel;  /* 3;  0 skips (segmentation.py:91)                            */
+    int32_t adapt_block;   /* 51  */
+    int32_t adapt_C;       /* 10  */
+    int32_t defect_method; /* 0 threshold (default), 1 canny                              */
+    int32_t threshold;     /* 24  */
+    int32_t min_area;      /* 20  */
+    int32_t erode_px;      /* 6   */
+    int32_t median_ksize;  /* 21 (hard-coded in the reference, indexing_ui.py:1522)       */
+    double max_area_frac;  /* 0.98 (indexing_ui.py:1548)                                  */
+} vi_params;
+
+/* One record per (image, unit), 64 bytes. */
+typedef struct vi_unit_record {
+    int32_t image;       /* image index in the batch                                      */
+    int32_t unit;        /* position in the grid list (the reference's loop index)       */
+    int32_t otsu_t;      /* Otsu threshold of the blurred crop (segmentation.py:82)      */
+    int32_t seg_area;    /* #(seg mask > 0) after exclusions (indexing_ui.py:1491)       */
+    int32_t roi_area;    /* after erosion + largest 8-CC (indexing_ui.py:1545)           */
+    int32_t defect_area; /* mask_stats(defect)['area'] (indexing_ui.py:1615, :1697)      */
+    int32_t n_kept;      /* contours that passed the area filter (indexing_ui.py:1551)   */
+    int32_t status;      /* VI_STATUS_*                                                   */
+    int32_t dx, dy;      /* centroid shift applied to exclusions (indexing_ui.py:2310)   */
+    double cx, cy;       /* pre-exclusion largest-8CC centroid, NaN if none (:2285,:2296) */
+    int32_t n_ambiguous; /* diagnostics: ROI pixels that needed an exact rank count      */
+    int32_t n_runs;      /* diagnostics: max run count seen by the labelling passes      */
+} vi_unit_record;
+
+const char* vi_last_error(void);
+int vi_version(void);
+
+void vi_params_default(vi_params* p);
+
+int vi_ctx_create(int device, vi_ctx** out);
+void vi_ctx_destroy(vi_ctx* ctx);
+
+/* Grid rectangles, image-space (x,y,w,h) in list order: the `boxes` of grid
+ * JSON v2 (indexing_ui.py:2739-2742, :2881-2889) / update_grid_preview (:2184-2191). */
+int vi_set_grid(vi_ctx* ctx, const int32_t* rects_xywh, int n_units);
+/* `exclusions` of grid JSON v2 (indexing_ui.py:2316-2338). n = 0 clears. */
+int vi_set_exclusions(vi_ctx* ctx, const vi_excl* excl, int n);
+/* exclusion_alignment.ref_centroids (indexing_ui.py:2856-2871): [n_units][2]
+ * doubles (cx,cy), NaN = absent.  is_reference != 0 means the batch IS the
+ * reference image (indexing_ui.py:2259): shifts are 0.  NULL clears. */
+int vi_set_ref_centroids(vi_ctx* ctx, const double* cxcy, int n_units, int is_reference);
+
+/* Sum of w*h over the grid, and the prefix sums (n_units+1 entries) that locate
+ * each unit's packed mask inside one image's mask block. */
+int64_t vi_unit_pixels(vi_ctx* ctx);
+int vi_unit_offsets(vi_ctx* ctx, int64_t* out_offsets);
+
+/* The hot path: run_segmentation_all (indexing_ui.py:2268-2338) followed by
+ * run_inspection (indexing_ui.py:1669-1702) for every unit of every image.
+ * d_frames: device, uint8 mono, image i at d_frames + i*image_stride, rows
+ * row_pitch bytes apart.  Outputs (device): masks packed per unit in grid order,
+ * image-major, values 0/255 (mask of image i, unit u starts at
+ * i*vi_unit_pixels + offsets[u]); d_labels (optional, may be NULL): int32
+ * raster-canonical 8-connected labels of the eroded ROI source (the labelling at
+ * indexing_ui.py:1505), same packing; d_records: [n_images*n_units].
+ * Asynchronous on `stream` (a cudaStream_t). */
+int vi_inspect_batch(vi_ctx* ctx, const uint8_t* d_frames, int n_images, int W, int H,
+                     int64_t row_pitch, int64_t image_stride, const vi_params* params,
+                     uint8_t* d_seg_masks, uint8_t* d_defect_masks, int32_t* d_labels_or_null,
+                     vi_unit_record* d_records, void* stream);
+
+/* Same, from and to HOST buffers (pinned memory recommended): uploads frames in
+ * chunks, overlaps copy and compute on internal streams, downloads masks and
+ * records; blocks until done.  h_seg_masks / h_defect_masks may be NULL to skip
+ * that download.  This is the end-to-end call bench.py times as `e2e`. */
+int vi_inspect_batch_host(vi_ctx* ctx, const uint8_t* h_frames, int n_images, int W, int H,
+                          int64_t row_pitch, int64_t image_stride, const vi_params* params,
+                          uint8_t* h_seg_masks, uint8_t* h_defect_masks, vi_unit_record* h_records);
+
+/* ---- per-unit compat entry points (host pointers, synchronous) ------------ */
+
+/* segmentation.segment_cell (segmentation.py:75-100): gray [h][w] -> mask 0/255. */
+int vi_segment_cell(vi_ctx* ctx, const uint8_t* gray, int h, int w, const vi_params* params,
+                    uint8_t* out_mask, int32_t* out_otsu_t);
+/* segmentation.fill_internal_holes (segmentation.py:27-72). */
+int vi_fill_internal_holes(vi_ctx* ctx, const uint8_t* mask, int h, int w, uint8_t* out_mask);
+/* segmentation.mask_stats (segmentation.py:103-111): area, sum of x, sum of y of
+ * mask>0 (the caller divides in double, as numpy's mean does). */
+int vi_mask_stats(vi_ctx* ctx, const uint8_t* mask, int h, int w, int64_t* area, int64_t* sum_x,
+                  int64_t* sum_y);
+/* cv2.erode(mask, None, iterations=r) on a binarised mask (indexing_ui.py:1497). */
+int vi_erode_square(vi_ctx* ctx, const uint8_t* mask, int h, int w, int r, uint8_t* out_mask);
+/* cv2.connectedComponentsWithStats(conn=8) + argmax area (indexing_ui.py:1505-1510,
+ * :2240-2248): labels in raster-canonical order (may be NULL), the chosen
+ * component's canonical label, area and coordinate sums. n_labels excludes 0. */
+int vi_label_components(vi_ctx* ctx, const uint8_t* mask, int h, int w, int32_t* out_labels,
+                        int32_t* n_labels, int32_t* best_label, int64_t* best_area,
+                        int64_t* best_sum_x, int64_t* best_sum_y);
+/* MainWindow._detect_defects_on_pix (indexing_ui.py:1471-1572) minus Qt:
+ * *found = 0 means the reference returns None (out_mask is then all zero). */
+int vi_detect_defects(vi_ctx* ctx, const uint8_t* gray, const uint8_t* seg_mask, int h, int w,
+                      const vi_params* params, uint8_t* out_mask, int32_t* found,
+                      vi_unit_record* out_record_or_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VI_B200_H */

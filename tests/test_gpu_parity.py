@@ -1,0 +1,276 @@
+"""CUDA path (through the C ABI) against the CPU oracle and the reference goldens.
+Run on the B200 box: python -m pytest tests -m gpu"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+cv2 = pytest.importorskip("cv2")
+
+from oracle import ref_cv2 as R
+from oracle import restate as S
+import vi_b200
+from vi_b200 import synth
+from vi_b200.grid import Grid
+
+
+@pytest.fixture(scope="module")
+def insp():
+    return vi_b200.Inspector(0)
+
+
+def crops(n=3, seed0=500, shape=(315, 316)):
+    h, w = shape
+    out = []
+    for s in range(n):
+        fr = synth.make_frame(seed0 + s, [(8, 8, w, h)], H=h + 16, W=w + 16)
+        out.append(fr[8:8 + h, 8:8 + w].copy())
+    return out
+
+
+def adversarial_masks():
+    rng = np.random.default_rng(5)
+    ms = [np.zeros((17, 23), np.uint8), np.full((17, 23), 255, np.uint8), np.full((1, 1), 255, np.uint8),
+          np.zeros((1, 40), np.uint8)]
+    m = np.zeros((40, 40), np.uint8); m[5:35, 5:35] = 255; m[10:30, 10:30] = 0; m[15:25, 15:25] = 255; m[18:22, 18:22] = 0
+    ms.append(m)
+    m = np.zeros((30, 30), np.uint8); np.fill_diagonal(m, 255); ms.append(m)
+    m = np.zeros((30, 31), np.uint8); m[::2, ::2] = 255; m[1::2, 1::2] = 255; ms.append(m)
+    m = np.zeros((30, 30), np.uint8); m[0, :] = m[-1, :] = 255; m[:, 0] = m[:, -1] = 255; m[10:14, 10:14] = 255; ms.append(m)
+    m = np.zeros((33, 35), np.uint8); m[16, :] = 255; m[:, 17] = 255; ms.append(m)
+    m = np.zeros((12, 12), np.uint8); m[2:5, 2:5] = 255; m[5:8, 5:8] = 255; ms.append(m)
+    m = np.zeros((20, 20), np.uint8); m[4:16, 4:16] = 255; m[6:14, 6:14] = 0; m[9, 4:6] = 0; ms.append(m)
+    m = np.zeros((20, 40), np.uint8); m[10:14, 2:6] = 255; m[3:7, 30:34] = 255; ms.append(m)      # area tie
+    m = np.zeros((21, 40), np.uint8); m[5:9, 30:34] = 255; m[4:8, 2:6] = 255; m[4, 2] = 0; m[8, 5] = 255; ms.append(m)
+    ms.append((rng.random((200, 210)) < 0.02).astype(np.uint8) * 255)
+    ms.append((rng.random((150, 160)) < 0.55).astype(np.uint8) * 255)
+    ms.append((rng.random((315, 316)) < 0.5).astype(np.uint8) * 255)      # run table overflows shared memory
+    ms.append((rng.random((64, 70)) < 0.3).astype(np.uint8) * 7)          # non-255 foreground values
+    m = np.zeros((315, 316), np.uint8); m[::2, ::2] = 255; ms.append(m)   # maximal run count
+    # spiral: long dependency chains for the union-find
+    m = np.zeros((101, 101), np.uint8)
+    x = y = 0; dx, dy = 1, 0; n = 101
+    lo_x, hi_x, lo_y, hi_y = 0, 100, 0, 100
+    while lo_x <= hi_x and lo_y <= hi_y:
+        m[lo_y, lo_x:hi_x + 1] = 255; m[lo_y:hi_y + 1, hi_x] = 255
+        if hi_y - lo_y >= 2: m[hi_y, lo_x + 2:hi_x + 1] = 255
+        if hi_x - lo_x >= 2: m[lo_y + 2:hi_y + 1, lo_x + 2] = 255
+        lo_x += 4; lo_y += 4; hi_x -= 4; hi_y -= 4
+    ms.append(m)
+    return ms
+
+
+@pytest.mark.parametrize("r", [0, 1, 2, 3, 6, 7, 17, 40, 63, 200])
+def test_erode_square(insp, r):
+    for m in adversarial_masks() + [R.segment_cell(c) for c in crops(2)]:
+        ref = cv2.erode(((m > 0) * 255).astype(np.uint8), None, iterations=r) if r > 0 else ((m > 0) * 255).astype(np.uint8)
+        got = insp.erode_square(m, r)
+        assert np.array_equal(got, ref), (r, m.shape, int((got != ref).sum()))
+
+
+def test_fill_internal_holes(insp):
+    for m in adversarial_masks():
+        ref = R.fill_internal_holes(m)
+        got = insp.fill_internal_holes(m)
+        assert np.array_equal(got, ref), (m.shape, int((got != ref).sum()))
+
+
+def test_mask_stats(insp):
+    from vi_b200 import segmentation as seg
+    for m in adversarial_masks():
+        assert seg.mask_stats(m) == R.mask_stats(m)
+
+
+def test_label_components(insp):
+    for m in adversarial_masks():
+        res = insp.label_components(m)
+        lab_ref, n_ref = S.label8(m)
+        assert res["n"] == n_ref
+        assert np.array_equal(res["labels"], lab_ref), m.shape
+        src = (m > 0).astype(np.uint8)
+        nlab, labels, stats, _ = cv2.connectedComponentsWithStats(src, connectivity=8)
+        if nlab <= 1:
+            assert res["best_label"] == 0 and res["centroid"] is None
+            continue
+        best = 1 + int(np.argmax(stats[1:, cv2.CC_STAT_AREA]))
+        assert np.array_equal(res["labels"] == res["best_label"], labels == best), m.shape
+        assert res["best_area"] == int(stats[best, cv2.CC_STAT_AREA])
+        assert res["centroid"] == R.largest_component_centroid(m)
+
+
+SEG_CFGS = [dict(), dict(gaussian_blur=5, morph_kernel=5), dict(gaussian_blur=0, morph_kernel=0),
+            dict(gaussian_blur=4, morph_kernel=2), dict(gaussian_blur=7, morph_kernel=7),
+            dict(gaussian_blur=31, morph_kernel=9), dict(gaussian_blur=1, morph_kernel=1),
+            dict(gaussian_blur=2, morph_kernel=4), dict(method='bogus')]
+
+
+@pytest.mark.parametrize("ki", range(len(SEG_CFGS)))
+def test_segment_cell(insp, ki):
+    from vi_b200 import segmentation as seg
+    rng = np.random.default_rng(3)
+    imgs = crops(3) + [rng.integers(0, 256, size=(64, 97), dtype=np.uint8), np.full((40, 50), 123, np.uint8),
+                       np.tile(np.linspace(0, 255, 120).astype(np.uint8), (90, 1)),
+                       rng.integers(0, 256, size=(12, 15), dtype=np.uint8), rng.integers(0, 256, size=(1, 1), dtype=np.uint8),
+                       rng.integers(0, 256, size=(3, 200), dtype=np.uint8)]
+    kw = SEG_CFGS[ki]
+    for im in imgs:
+        ref = R.segment_cell(im, **kw)
+        got = seg.segment_cell(im, **kw)
+        assert got.flags.writeable and got.dtype == np.uint8
+        assert np.array_equal(got, ref), (kw, im.shape, int((got != ref).sum()))
+
+
+def test_otsu_threshold(insp):
+    rng = np.random.default_rng(0)
+    for i in range(40):
+        if i % 2:
+            im = rng.integers(0, 256, size=(40, 50), dtype=np.uint8)
+        else:
+            a, b = rng.integers(0, 256, size=2)
+            im = np.where(rng.random((60, 70)) < rng.random(), a, b).astype(np.uint8)
+            im = np.clip(im + rng.normal(0, rng.integers(1, 20), im.shape), 0, 255).astype(np.uint8)
+        p = vi_b200.default_params(gaussian_blur=0, morph_kernel=0)
+        _, t = insp.segment_cell(im, p, return_threshold=True)
+        assert t == R.otsu_threshold(im), i
+
+
+@pytest.mark.parametrize("cfg", [(6, 24, 20), (1, 8, 0), (40, 3, 5), (0, 24, 20), (6, 0, 0), (6, 255, 0), (200, 24, 20),
+                                 (3, 12, 1)])
+def test_detect_defects(insp, cfg):
+    r, thr, mn = cfg
+    rng = np.random.default_rng(9)
+    excl = [{'shape': 'rect', 'x': 50, 'y': 60, 'w': 70, 'h': 30}, {'shape': 'circle', 'cx': 200, 'cy': 180, 'r': 25}]
+    cases = []
+    for gray in crops(3, seed0=600):
+        seg = R.segment_cell(gray)
+        R.apply_exclusions(seg, excl, 2, -3)
+        cases.append((gray, seg))
+    g = rng.integers(0, 256, size=(96, 96), dtype=np.uint8)
+    cases.append((g, np.full((96, 96), 255, np.uint8)))                    # uniform noise: every pixel needs the exact rank count
+    g2 = crops(1, seed0=610, shape=(60, 340))[0]
+    cases.append((g2, np.full(g2.shape, 255, np.uint8)))                   # wider than the fast rank-count pass
+    g3 = rng.integers(0, 256, size=(12, 15), dtype=np.uint8)
+    cases.append((g3, np.full(g3.shape, 255, np.uint8)))                   # smaller than the median window
+    p = vi_b200.default_params(threshold=thr, min_area=mn, erode_px=r)
+    for gray, seg in cases:
+        info = {}
+        ref = R.detect_defects(gray, seg, 'threshold', thr, mn, r, info)
+        got, rec = insp.detect_defects(gray, seg, p, return_record=True)
+        assert (ref is None) == (got is None), (cfg, gray.shape)
+        if ref is not None:
+            assert np.array_equal(got, ref), (cfg, gray.shape, int((got != ref).sum()))
+            assert rec["defect_area"] == int((ref > 0).sum())
+            assert rec["n_kept"] == info["n_kept"]
+        if 'roi' in info:
+            assert rec["roi_area"] == int((info['roi'] > 0).sum())
+
+
+def _run_batch(insp, g, fi, params, is_reference, refc, exclusions, host=False, labels=False):
+    import torch
+    grid = Grid(boxes=g.boxes, exclusions=exclusions, ref_centroids=refc or {})
+    insp.configure(grid, is_reference=is_reference)
+    frame = g.frame(fi)
+    if host:
+        rec, seg, dfm = insp.inspect_batch_host(frame[None], params)
+        return rec, seg, dfm, None
+    d = torch.from_numpy(frame[None]).cuda()
+    lab = torch.empty(insp.unit_pixels, dtype=torch.int32, device="cuda") if labels else None
+    rec, seg, dfm = insp.inspect_batch(d, params, labels=lab)
+    torch.cuda.synchronize()
+    rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    return rec, seg.cpu().numpy(), dfm.cpu().numpy(), (lab.cpu().numpy() if labels else None)
+
+
+@pytest.mark.parametrize("name", ["config1", "config4", "config5", "blur5_morph5"])
+def test_batch_matches_reference_goldens(insp, golden, name):
+    g = golden(name)
+    meta = g.meta
+    refc = {i: (float(c[0]), float(c[1])) for i, c in enumerate(g.z['ref_centroids']) if not np.isnan(c[0])}
+    pk = {k: v for k, v in meta['params'].items()}
+    for fi in range(len(meta['seeds'])):
+        seg_gold = g.masks(f'f{fi}_seg')
+        for r in meta['erode_list']:
+            p = vi_b200.default_params(**{**pk, 'erode_px': r})
+            rec, seg, dfm, _ = _run_batch(insp, g, fi, p, fi == 0, None if fi == 0 else refc, meta['exclusions'])
+            segs = insp.split_masks(seg)
+            defs = insp.split_masks(dfm)
+            dgold = g.defects(fi, r)
+            ng = g.z[f'f{fi}_r{r}_ng']
+            area = g.z[f'f{fi}_r{r}_area']
+            for i in range(len(g.boxes)):
+                assert np.array_equal(segs[i], seg_gold[i]), (name, fi, r, i, 'seg', int((segs[i] != seg_gold[i]).sum()))
+                if dgold[i] is None:
+                    assert rec[i]['n_kept'] == 0 and not defs[i].any(), (name, fi, r, i)
+                else:
+                    assert rec[i]['n_kept'] > 0
+                    assert np.array_equal(defs[i], dgold[i]), (name, fi, r, i, 'defect', int((defs[i] != dgold[i]).sum()))
+                assert rec[i]['defect_area'] == area[i], (name, fi, r, i)
+                assert (rec[i]['status'] == vi_b200.STATUS_NG) == bool(ng[i]), (name, fi, r, i)
+                assert rec[i]['unit'] == i and rec[i]['image'] == 0
+            if fi == 0:
+                for i in range(len(g.boxes)):
+                    assert rec[i]['cx'] == g.z['ref_centroids'][i][0] and rec[i]['cy'] == g.z['ref_centroids'][i][1]
+
+
+def test_batch_matches_oracle_records_and_labels(insp, golden):
+    """Every record field and the raster-canonical ROI labels against the cv2 oracle."""
+    g = golden('config4')
+    meta = g.meta
+    refc = {i: (float(c[0]), float(c[1])) for i, c in enumerate(g.z['ref_centroids']) if not np.isnan(c[0])}
+    p = vi_b200.default_params(erode_px=17)
+    rec, seg, dfm, lab = _run_batch(insp, g, 1, p, False, refc, meta['exclusions'], labels=True)
+    recs, segs, defs = R.inspect_frame(g.frame(1), g.boxes, R.Params(erode_px=17), meta['exclusions'], refc, False)
+    labs = insp.split_masks(lab)
+    for i, o in enumerate(recs):
+        for k in ('seg_area', 'roi_area', 'defect_area', 'n_kept', 'status', 'dx', 'dy'):
+            assert rec[i][k] == o[k], (i, k, rec[i][k], o[k])
+        assert rec[i]['cx'] == o['cx'] and rec[i]['cy'] == o['cy']
+        gray = g.frame(1)[g.boxes[i][0][1]:g.boxes[i][0][1] + 315, g.boxes[i][0][0]:g.boxes[i][0][0] + 316]
+        assert rec[i]['otsu_t'] == R.otsu_threshold(cv2.GaussianBlur(gray, (3, 3), 0))
+        er = cv2.erode(((segs[i] > 0) * 255).astype(np.uint8), None, iterations=17)
+        lab_ref, _ = S.label8(er)
+        assert np.array_equal(labs[i], lab_ref), i
+
+
+def test_host_batch_equals_device_batch(insp, golden):
+    import torch
+    g = golden('config1')
+    grid = Grid(boxes=g.boxes)
+    insp.configure(grid, is_reference=True)
+    frames = np.stack([g.frame(0), synth.make_frame(11, [b for b, _ in g.boxes]), synth.make_frame(12, [b for b, _ in g.boxes])])
+    rec_h, seg_h, def_h = insp.inspect_batch_host(frames)
+    rec_d, seg_d, def_d = insp.inspect_batch(torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    rec_d = rec_d.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    assert np.array_equal(seg_h, seg_d.cpu().numpy()) and np.array_equal(def_h, def_d.cpu().numpy())
+    for k in vi_b200.RECORD_DTYPE.names:
+        a, b = rec_h[k], rec_d[k]
+        assert np.array_equal(a, b) or (a.dtype.kind == 'f' and np.array_equal(np.isnan(a), np.isnan(b))), k
+    assert list(rec_h['image']) == [i for i in range(3) for _ in range(48)]
+    # frames 11 and 12 against the oracle
+    for fi in (1, 2):
+        recs, segs, defs = R.inspect_frame(frames[fi], g.boxes, R.Params(), (), None, True)
+        sm = insp.split_masks(seg_h, fi); dm = insp.split_masks(def_h, fi)
+        for i in range(48):
+            assert np.array_equal(sm[i], segs[i])
+            assert np.array_equal(dm[i], defs[i] if defs[i] is not None else np.zeros_like(dm[i]))
+            assert rec_h[fi * 48 + i]['status'] == recs[i]['status']
+
+
+def test_error_paths(insp):
+    from vi_b200 import segmentation as seg
+    assert seg.fill_internal_holes(None) is None
+    with pytest.raises(ValueError):
+        seg.fill_internal_holes(np.zeros((2, 2, 2), np.uint8))
+    assert seg.mask_stats(np.zeros((4, 4), np.uint8)) == {'area': 0, 'centroid': (0, 0)}
+    with pytest.raises(vi_b200.ViError):
+        seg.segment_cell(np.zeros((8, 8), np.uint8), method='adaptive')     # not built yet: fails loudly
+    with pytest.raises(vi_b200.ViError):
+        insp.set_grid([(0, 0, 2000, 2000)])                                  # does not fit shared memory
+    insp.set_grid([(10, 10, 50, 50)])
+    import torch
+    with pytest.raises(vi_b200.ViError):
+        insp.inspect_batch(torch.zeros((1, 40, 40), dtype=torch.uint8, device='cuda'))   # rect leaves the frame

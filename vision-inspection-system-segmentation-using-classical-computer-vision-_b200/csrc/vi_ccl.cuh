@@ -1,0 +1,279 @@
+// vi_ccl.cuh -- run-based connected-component labelling of a bit-packed mask
+// inside one CTA.  A "run" is a maximal horizontal span of set pixels; runs are
+// numbered 1..R in raster order (node 0 is the virtual "outside the crop" node
+// used by the hole fill).  Union-find over runs:
+//   A  link every run to the first overlapping run of the row above,
+//   B  pointer jumping,
+//   C  lock-free unions for every further overlap (and with node 0 for runs
+//      that touch the crop border when `border` is set),
+//   D  pointer jumping.
+// After build, parent[i] is the smallest run id of i's component -- the run that
+// holds the component's first pixel in raster order, so ranking roots by id gives
+// the raster-canonical label order.
+//
+// Used five times per unit: background 4-connected hole fill (segmentation.py:
+// 27-72 and the hole filling implied by drawContours(FILLED), indexing_ui.py:1554),
+// largest 8-connected component (indexing_ui.py:2240-2248, :1505-1510) and the
+// per-component contour-area filter (indexing_ui.py:1540-1558).
+#pragma once
+#include "vi_device.cuh"
+
+namespace vi {
+
+struct CclWs {
+    unsigned short* xs;   // [cap+1]
+    unsigned short* xe;   // [cap+1]
+    unsigned short* yy;   // [cap+1]
+    int* parent;          // [cap+1]
+    unsigned* acc0;       // [cap+1] per-root accumulator
+    unsigned* acc1;       // [cap+1] per-root accumulator
+    int* row_first;       // [h+2] first run id of each row; row_first[h] = R+1
+    int cap;
+};
+
+__host__ __device__ inline size_t ccl_ws_bytes(int cap, int h) {
+    return (size_t)align16((h + 2) * 4) + (size_t)(cap + 1) * 18 + 64;
+}
+
+__device__ inline CclWs ccl_ws_carve(unsigned char* base, int cap, int h) {
+    CclWs ws;
+    ws.row_first = reinterpret_cast<int*>(base);
+    unsigned char* p = base + align16((h + 2) * 4);
+    ws.parent = reinterpret_cast<int*>(p); p += (size_t)(cap + 1) * 4;
+    ws.acc0 = reinterpret_cast<unsigned*>(p); p += (size_t)(cap + 1) * 4;
+    ws.acc1 = reinterpret_cast<unsigned*>(p); p += (size_t)(cap + 1) * 4;
+    ws.xs = reinterpret_cast<unsigned short*>(p); p += (size_t)(cap + 1) * 2;
+    ws.xe = reinterpret_cast<unsigned short*>(p); p += (size_t)(cap + 1) * 2;
+    ws.yy = reinterpret_cast<unsigned short*>(p);
+    ws.cap = cap;
+    return ws;
+}
+
+__device__ __forceinline__ int uf_find(const volatile int* parent, int x) {
+    int p = parent[x];
+    while (p != x) { x = p; p = parent[x]; }
+    return x;
+}
+
+__device__ inline void uf_unite(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicCAS(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+
+__device__ inline void ccl_jump(int* parent, int R) {
+    // pointer jumping until every node points at its root
+    while (true) {
+        int changed = 0;
+        for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {
+            int p = parent[i];
+            int pp = parent[p];
+            if (pp != p) { parent[i] = pp; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+}
+
+// Start / end bit masks of the runs inside word c of row y.
+__device__ __forceinline__ void run_edges(const unsigned* M, const Geom& g, int y, int c, unsigned& starts, unsigned& ends) {
+    unsigned m = M[y * g.wpr + c];
+    unsigned prev = c > 0 ? M[y * g.wpr + c - 1] : 0u;
+    unsigned next = c < g.wpr - 1 ? M[y * g.wpr + c + 1] : 0u;
+    starts = m & ~((m << 1) | (prev >> 31));
+    ends = m & ~((m >> 1) | (next << 31));
+}
+
+// Builds runs + components of mask M.  ws_s (shared) is used when the runs fit,
+// else ws_g (global scratch).  Returns R (run count) and the workspace used.
+__device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
+                                const CclWs& ws_s, const CclWs& ws_g, CclWs& ws) {
+    const int per = (g.nwords + kThreads - 1) / kThreads;
+    const int i0 = threadIdx.x * per;
+    const int i1 = min(i0 + per, g.nwords);
+    unsigned ns = 0, ne = 0;
+    for (int i = i0; i < i1; ++i) {
+        int y = i / g.wpr, c = i - y * g.wpr;
+        unsigned s, e;
+        run_edges(M, g, y, c, s, e);
+        ns += __popc(s);
+        ne += __popc(e);
+    }
+    unsigned os = ns, oe = ne, R, Re;
+    cta_excl_scan2(cs, os, oe, R, Re);
+    ws = ((int)R <= ws_s.cap) ? ws_s : ws_g;
+    for (int i = i0; i < i1; ++i) {
+        int y = i / g.wpr, c = i - y * g.wpr;
+        unsigned s, e;
+        run_edges(M, g, y, c, s, e);
+        if (c == 0) ws.row_first[y] = (int)os + 1;
+        while (s) {
+            int b = __ffs(s) - 1; s &= s - 1;
+            ++os;
+            ws.xs[os] = (unsigned short)(c * 32 + b);
+            ws.yy[os] = (unsigned short)y;
+        }
+        while (e) {
+            int b = __ffs(e) - 1; e &= e - 1;
+            ++oe;
+            ws.xe[oe] = (unsigned short)(c * 32 + b);
+        }
+    }
+    if (threadIdx.x == 0) { ws.row_first[g.h] = (int)R + 1; ws.parent[0] = 0; ws.acc0[0] = 0; ws.acc1[0] = 0; }
+    __syncthreads();
+    const int c8 = conn8 ? 1 : 0;
+    // A: primary link = first overlapping run of the row above
+    for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
+        int y = ws.yy[i];
+        int link = i;
+        if (y > 0) {
+            int j0 = ws.row_first[y - 1], j1 = ws.row_first[y];
+            int xs = ws.xs[i], xe = ws.xe[i];
+            int lo = j0, hi = j1;            // first j with xe[j] >= xs - c8
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((int)ws.xe[mid] < xs - c8) lo = mid + 1; else hi = mid;
+            }
+            if (lo < j1 && (int)ws.xs[lo] <= xe + c8) link = lo;
+        }
+        ws.parent[i] = link;
+        ws.acc0[i] = 0;
+        ws.acc1[i] = 0;
+    }
+    __syncthreads();
+    ccl_jump(ws.parent, (int)R);
+    // C: remaining overlaps and the border link
+    for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
+        int y = ws.yy[i];
+        int xs = ws.xs[i], xe = ws.xe[i];
+        if (y > 0) {
+            int j0 = ws.row_first[y - 1], j1 = ws.row_first[y];
+            int lo = j0, hi = j1;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((int)ws.xe[mid] < xs - c8) lo = mid + 1; else hi = mid;
+            }
+            for (int j = lo + 1; j < j1 && (int)ws.xs[j] <= xe + c8; ++j) uf_unite(ws.parent, i, j);
+        }
+        if (border && (y == 0 || y == g.h - 1 || xs == 0 || xe == g.w - 1)) uf_unite(ws.parent, i, 0);
+    }
+    __syncthreads();
+    ccl_jump(ws.parent, (int)R);
+    return (int)R;
+}
+
+// Warp-aggregated per-root accumulation: lanes whose root equals the first valid
+// lane's root are reduced with REDUX and added once; the rest add individually.
+__device__ __forceinline__ void agg_add(unsigned* acc, bool valid, int root, unsigned val) {
+    unsigned vm = __ballot_sync(kFull, valid);
+    if (vm == 0) return;
+    int lead = __shfl_sync(kFull, root, __ffs(vm) - 1);
+    bool same = valid && root == lead;
+    unsigned sum = __reduce_add_sync(kFull, same ? val : 0u);
+    if (lane_id() == 0 && sum) atomicAdd(&acc[lead], sum);
+    if (valid && !same && val) atomicAdd(&acc[root], val);
+}
+
+__device__ __forceinline__ void agg_min(unsigned* acc, bool valid, int root, unsigned val) {
+    unsigned vm = __ballot_sync(kFull, valid);
+    if (vm == 0) return;
+    int lead = __shfl_sync(kFull, root, __ffs(vm) - 1);
+    bool same = valid && root == lead;
+    unsigned mn = __reduce_min_sync(kFull, same ? val : 0xffffffffu);
+    if (lane_id() == 0 && mn != 0xffffffffu) atomicMin(&acc[lead], mn);
+    if (valid && !same) atomicMin(&acc[root], val);
+}
+
+// dst[word] = OR of the spans of all runs of that row whose root satisfies pred,
+// optionally OR-ed with `base` (may be null).  Word-parallel, no atomics.
+template <class Pred>
+__device__ inline void ccl_paint(unsigned* dst, const unsigned* base, const Geom& g, const CclWs& ws, Pred pred) {
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+        int y = i / g.wpr, c = i - y * g.wpr;
+        int x0 = c * 32, x1 = x0 + 31;
+        int j0 = ws.row_first[y], j1 = ws.row_first[y + 1];
+        int lo = j0, hi = j1;                 // first run with xe >= x0
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if ((int)ws.xe[mid] < x0) lo = mid + 1; else hi = mid;
+        }
+        unsigned bits = 0;
+        for (int j = lo; j < j1; ++j) {
+            int xs = ws.xs[j];
+            if (xs > x1) break;
+            if (pred(ws.parent[j])) {
+                int xe = ws.xe[j];
+                bits |= bit_range(max(xs, x0) - x0, min(xe, x1) - x0);
+            }
+        }
+        dst[i] = base ? (base[i] | bits) : bits;
+    }
+}
+
+// rows 0..h-1 need row_first for every row, including rows without runs.
+// ccl_build writes row_first[y] only from the thread that owns word (y,0), which
+// exists for every row, so the table is always complete.
+
+// Largest component (max area; ties -> smallest 2x2-block key, i.e. OpenCV's label
+// order).  Returns the root id (0 if there is no run) and its area /
+// coordinate sums through the out-params.  Uses acc0 = area, acc1 = min block key.
+__device__ inline int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
+                                  unsigned& area, unsigned long long& sum_x, unsigned long long& sum_y) {
+    area = 0; sum_x = 0; sum_y = 0;
+    if (R == 0) return 0;
+    const int Rpad = (R + kThreads - 1) / kThreads * kThreads;
+    for (int base = 0; base < Rpad; base += kThreads) {
+        int i = base + threadIdx.x + 1;
+        bool valid = i <= R;
+        int root = valid ? ws.parent[i] : 0;
+        unsigned len = valid ? (unsigned)(ws.xe[i] - ws.xs[i] + 1) : 0u;
+        agg_add(ws.acc0, valid, root, len);
+    }
+    __syncthreads();
+    unsigned long long best = 0;
+    for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
+        if (ws.parent[i] == i) {
+            unsigned long long a = ws.acc0[i];
+            best = a > best ? a : best;
+        }
+    unsigned amax = (unsigned)cta_max_u64(cs, best);
+    // min block key among the components of maximal area
+    const int w2 = (g.w + 1) / 2;
+    for (int i = 1 + threadIdx.x; i <= R; i += kThreads) ws.acc1[i] = 0xffffffffu;
+    __syncthreads();
+    for (int base = 0; base < Rpad; base += kThreads) {
+        int i = base + threadIdx.x + 1;
+        bool valid = i <= R;
+        int root = valid ? ws.parent[i] : 0;
+        valid = valid && ws.acc0[root] == amax;
+        unsigned key = valid ? (unsigned)((ws.yy[i] >> 1) * w2 + (ws.xs[i] >> 1)) : 0xffffffffu;
+        agg_min(ws.acc1, valid, root, key);
+    }
+    __syncthreads();
+    unsigned long long sel = 0;   // pick (min key) -> encode as max of (~key, root)
+    for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
+        if (ws.parent[i] == i && ws.acc0[i] == amax) {
+            unsigned long long v = ((unsigned long long)(0xffffffffu - ws.acc1[i]) << 32) | (unsigned)i;
+            sel = v > sel ? v : sel;
+        }
+    sel = cta_max_u64(cs, sel);
+    int broot = (int)(sel & 0xffffffffu);
+    unsigned long long sx = 0, sy = 0;
+    for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
+        if (ws.parent[i] == broot) {
+            unsigned long long xs = ws.xs[i], xe = ws.xe[i];
+            unsigned long long len = xe - xs + 1;
+            sx += (xs + xe) * len / 2;
+            sy += (unsigned long long)ws.yy[i] * len;
+        }
+    sum_x = cta_sum_u64(cs, sx);
+    sum_y = cta_sum_u64(cs, sy);
+    area = amax;
+    return broot;
+}
+
+}  // namespace vi

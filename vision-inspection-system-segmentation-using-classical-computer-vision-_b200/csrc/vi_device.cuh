@@ -1,0 +1,361 @@
+// vi_device.cuh -- device-side building blocks of the fused per-unit inspection
+// kernel (sm_100a).  One CTA owns one unit at a time; the unit's gray crop and
+// all of its masks (bit-packed, 32 px per word) live in shared memory from the
+// crop gather to the verdict, so HBM sees 1 B/px in and 2 B/px out.
+//
+// Reference semantics: SURVEY.md Appendix A; every stage cites the reference
+// call site it reproduces (paths under the reference tree).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/vi_b200.h"
+
+namespace vi {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kHistWords = 2048;   // per-warp lane-private histogram: [64 bin-quads][32 lanes] u32, 4 x 8-bit counters
+constexpr int kHistBytes = kHistWords * 4;
+constexpr int kMaxExcl = 32;
+constexpr int kMaxTaps = 33;
+constexpr int kMaxSE = 33;
+constexpr int kLevels = 6;         // rank-count levels of the median stage (two words of three 10-bit fields)
+constexpr int kBandRows = 16;      // output rows per band of the rank-count stage
+constexpr int kSegL = 11;         // columns per lane in the horizontal prefix of the rank-count stage
+constexpr int kRankMaxW = 32 * kSegL - 20;   // widest unit the one-warp-per-row pass covers (332)
+constexpr int kNumMasks = 5;
+constexpr unsigned kFull = 0xffffffffu;
+
+enum Mode : int {
+    MODE_FULL = 0,      // segmentation + detector + verdict (the hot path)
+    MODE_SEG_ONLY = 1,  // segmentation.segment_cell
+    MODE_FILL = 2,      // segmentation.fill_internal_holes on aux mask
+    MODE_STATS = 3,     // segmentation.mask_stats on aux mask
+    MODE_ERODE = 4,     // cv2.erode(mask, None, iterations=r) on aux mask
+    MODE_LABEL = 5,     // connectedComponentsWithStats(8) on aux mask
+    MODE_DETECT = 6,    // _detect_defects_on_pix with aux mask as the seg mask
+};
+
+struct Geom {
+    int w, h;
+    int wpr;            // mask words per row
+    int gp;             // gray pitch in bytes (multiple of 4, odd word count)
+    int nwords;         // h * wpr
+    unsigned lastmask;  // valid bits of the last word of a row
+};
+
+__host__ __device__ inline int gray_pitch(int w) {
+    int words = (w + 3) / 4;
+    if ((words & 1) == 0) words += 1;   // odd pitch in words: row-strided access hits distinct banks
+    return words * 4;
+}
+
+__host__ __device__ inline Geom make_geom(int w, int h) {
+    Geom g;
+    g.w = w; g.h = h;
+    g.wpr = (w + 31) / 32;
+    g.gp = gray_pitch(w);
+    g.nwords = h * g.wpr;
+    int rem = w & 31;
+    g.lastmask = rem ? ((1u << rem) - 1u) : 0xffffffffu;
+    return g;
+}
+
+// Shared-memory plan for the largest unit of a grid (host computes, kernel follows).
+struct SmemPlan {
+    int gray_bytes;    // [0, gray_bytes): gray crop
+    int n_hist;        // lane-private histogram copies that fit next to the crop (1..16)
+    int mask_bytes;    // one bit-packed mask (16-B aligned)
+    int ws_bytes;      // workspace after the masks (run tables / Otsu arrays / rank-count band)
+    int run_cap;       // runs that fit the shared workspace
+    int band_pitch;    // uint2 entries per band row of the rank-count stage
+    int total;         // dynamic shared memory bytes
+};
+
+__host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
+
+__host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, SmemPlan* p) {
+    Geom g = make_geom(wmax, hmax);
+    p->gray_bytes = align16(g.gp * hmax);
+    p->mask_bytes = align16(g.nwords * 4);
+    int nseg = (wmax + 20 + kSegL - 1) / kSegL;
+    if (nseg > 32) nseg = 32;
+    p->band_pitch = nseg * kSegL;
+    int band = kBandRows * p->band_pitch * 8 + 256 * 8 + 256 * 2 + 64;
+    int otsu = 256 * 8 * 5 + 256 * 4 + 256;
+    int rowfirst = align16((hmax + 2) * 4);
+    int want_cap = 2048;
+    int ccl = rowfirst + (want_cap + 1) * 18 + 64;
+    int ws = band > otsu ? band : otsu;
+    if (ccl > ws) ws = ccl;
+    ws = align16(ws);
+    // `fixed`: the kernel's static shared memory (CTA histogram, scan scratch, scalars)
+    int avail = smem_limit - fixed - p->gray_bytes;
+    int need_r = kNumMasks * p->mask_bytes + ws;
+    if (avail < need_r || avail < kHistBytes) return false;
+    int nh = avail / kHistBytes;
+    if (nh > kWarps) nh = kWarps;
+    p->n_hist = nh;
+    int r_bytes = nh * kHistBytes;
+    if (r_bytes < need_r) r_bytes = need_r;
+    // spend what is left of the hist region on a larger run table
+    int spare = r_bytes - kNumMasks * p->mask_bytes;
+    if (spare > ws) ws = spare & ~15;
+    p->ws_bytes = ws;
+    p->run_cap = (ws - rowfirst - 64) / 18 - 1;
+    if (p->run_cap > 65534) p->run_cap = 65534;
+    p->total = p->gray_bytes + r_bytes;
+    return true;
+}
+
+struct KArgs {
+    const uint8_t* frames;
+    int n_images, W, H;
+    long long row_pitch, image_stride;
+    const int4* rects;
+    int n_units;
+    const long long* unit_off;      // [n_units+1]
+    long long unit_px;
+    const vi_excl* excl;
+    int n_excl;
+    const double* refc;             // [n_units][2] or null
+    int is_reference;
+    vi_params p;
+    int blur_k;                     // 0 skip, 3 fast path, else general (odd)
+    int taps[kMaxTaps];             // 8.8 fixed-point Gaussian taps for the general path
+    int se_k;                       // 0 skip, 3 = cross fast path, else general
+    signed char se_lo[kMaxSE], se_hi[kMaxSE];   // per SE row: x-offset span [lo,hi] relative to the anchor (lo>hi: empty)
+    uint8_t* seg_out;
+    uint8_t* def_out;
+    int32_t* labels_out;
+    vi_unit_record* rec;
+    const uint8_t* aux_mask;        // compat modes: input mask, packed like the outputs
+    long long* stats_out;           // compat modes: [n_total][4]
+    int mode;
+    int erode_r;                    // MODE_ERODE radius
+    uint8_t* scratch;               // per-CTA global scratch (general blur path, run-table overflow)
+    long long scratch_stride;
+    int wmax, hmax;
+    SmemPlan plan;
+};
+
+// ---------------------------------------------------------------------------
+// CTA-wide primitives
+// ---------------------------------------------------------------------------
+struct CtaScratch {
+    unsigned wa[kWarps];
+    unsigned wb[kWarps];
+    unsigned long long wl[kWarps];
+    unsigned tot_a, tot_b;
+    unsigned long long tot_l;
+    int flag;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// Exclusive scan of (a, b) over the CTA's threads; totals returned through ta/tb.
+__device__ inline void cta_excl_scan2(CtaScratch& cs, unsigned& a, unsigned& b, unsigned& ta, unsigned& tb) {
+    const int lane = lane_id(), warp = warp_id();
+    unsigned ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned xa = __shfl_up_sync(kFull, ia, o);
+        unsigned xb = __shfl_up_sync(kFull, ib, o);
+        if (lane >= o) { ia += xa; ib += xb; }
+    }
+    if (lane == 31) { cs.wa[warp] = ia; cs.wb[warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned va = lane < kWarps ? cs.wa[lane] : 0u;
+        unsigned vb = lane < kWarps ? cs.wb[lane] : 0u;
+        unsigned sa = va, sb = vb;
+#pragma unroll
+        for (int o = 1; o < kWarps; o <<= 1) {
+            unsigned xa = __shfl_up_sync(kFull, sa, o);
+            unsigned xb = __shfl_up_sync(kFull, sb, o);
+            if (lane >= o) { sa += xa; sb += xb; }
+        }
+        if (lane < kWarps) { cs.wa[lane] = sa - va; cs.wb[lane] = sb - vb; }
+        if (lane == kWarps - 1) { cs.tot_a = sa; cs.tot_b = sb; }
+    }
+    __syncthreads();
+    a = ia - a + cs.wa[warp];
+    b = ib - b + cs.wb[warp];
+    ta = cs.tot_a;
+    tb = cs.tot_b;
+    __syncthreads();
+}
+
+__device__ inline unsigned long long cta_sum_u64(CtaScratch& cs, unsigned long long v) {
+    const int lane = lane_id(), warp = warp_id();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
+    if (lane == 0) cs.wl[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long t = lane < kWarps ? cs.wl[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(kFull, t, o);
+        if (lane == 0) cs.tot_l = t;
+    }
+    __syncthreads();
+    unsigned long long r = cs.tot_l;
+    __syncthreads();
+    return r;
+}
+
+__device__ inline unsigned long long cta_max_u64(CtaScratch& cs, unsigned long long v) {
+    const int lane = lane_id(), warp = warp_id();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_down_sync(kFull, v, o);
+        v = x > v ? x : v;
+    }
+    if (lane == 0) cs.wl[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long t = lane < kWarps ? cs.wl[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long x = __shfl_down_sync(kFull, t, o);
+            t = x > t ? x : t;
+        }
+        if (lane == 0) cs.tot_l = t;
+    }
+    __syncthreads();
+    unsigned long long r = cs.tot_l;
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// Bit-packed mask rows.  Bit x&31 of word x>>5 is pixel x; bits >= w of the last
+// word of a row are always 0.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned row_mask_of(const Geom& g, int c) { return c == g.wpr - 1 ? g.lastmask : 0xffffffffu; }
+
+// Word c of row y; rows outside [0,h) and words outside [0,wpr) read as `fill`
+// (0 or ~0); with fill = ~0 the padding bits of the last word read as 1 too.
+__device__ __forceinline__ unsigned mword(const unsigned* M, const Geom& g, int y, int c, unsigned fill) {
+    if ((unsigned)y >= (unsigned)g.h || (unsigned)c >= (unsigned)g.wpr) return fill;
+    unsigned v = M[y * g.wpr + c];
+    if (c == g.wpr - 1) v |= fill & ~g.lastmask;
+    return v;
+}
+
+// Word c of row y shifted so that bit x takes the value of pixel x+dx
+// (dx may be negative); pixels outside [0,w) read as `fill`.
+__device__ __forceinline__ unsigned mword_shift(const unsigned* M, const Geom& g, int y, int c, int dx, unsigned fill) {
+    if (dx == 0) return mword(M, g, y, c, fill);
+    int bit0 = c * 32 + dx;                 // pixel index that lands on bit 0
+    int c0 = bit0 >> 5;                     // floor division (arithmetic shift)
+    int s = bit0 & 31;
+    unsigned lo = mword(M, g, y, c0, fill);
+    if (s == 0) return lo;
+    unsigned hi = mword(M, g, y, c0 + 1, fill);
+    return __funnelshift_r(lo, hi, s);
+}
+
+// Bits [a, b] (inclusive, 0 <= a <= b <= 31).
+__device__ __forceinline__ unsigned bit_range(int a, int b) {
+    unsigned hi = (b >= 31) ? 0xffffffffu : ((1u << (b + 1)) - 1u);
+    return hi & ~((1u << a) - 1u);
+}
+
+// One pass of a 3x3-cross erosion (out-of-crop = 1) or dilation (out-of-crop = 0):
+// cv2.getStructuringElement(MORPH_ELLIPSE,(3,3)) is the cross.
+template <bool ERODE>
+__device__ inline void cross3_pass(const unsigned* src, unsigned* dst, const Geom& g) {
+    const unsigned fill = ERODE ? 0xffffffffu : 0u;
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+        int y = i / g.wpr, c = i - y * g.wpr;
+        unsigned m = mword(src, g, y, c, fill);
+        unsigned l = mword_shift(src, g, y, c, -1, fill);
+        unsigned r = mword_shift(src, g, y, c, +1, fill);
+        unsigned u = mword(src, g, y - 1, c, fill);
+        unsigned d = mword(src, g, y + 1, c, fill);
+        unsigned o = ERODE ? (m & l & r & u & d) : (m | l | r | u | d);
+        dst[i] = o & row_mask_of(g, c);
+    }
+}
+
+// General structuring element given as per-row x-offset spans (the ellipse of
+// segmentation.py:93).  erode: AND over offsets, outside = 1; dilate: OR over the
+// same (un-reflected) offsets, outside = 0.
+template <bool ERODE>
+__device__ inline void se_pass(const unsigned* src, unsigned* dst, const Geom& g, int k,
+                               const signed char* lo, const signed char* hi) {
+    const unsigned fill = ERODE ? 0xffffffffu : 0u;
+    const int a = k / 2;
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+        int y = i / g.wpr, c = i - y * g.wpr;
+        unsigned o = fill;
+        for (int j = 0; j < k; ++j) {
+            int ys = y + j - a;
+            if (lo[j] > hi[j]) continue;
+            if ((unsigned)ys >= (unsigned)g.h) continue;   // out-of-crop rows never constrain either op
+            for (int dx = lo[j]; dx <= hi[j]; ++dx) {
+                unsigned v = mword_shift(src, g, ys, c, dx, fill);
+                o = ERODE ? (o & v) : (o | v);
+            }
+        }
+        dst[i] = o & row_mask_of(g, c);
+    }
+}
+
+// Replicate-clamped variants: pixels / rows outside the crop read as the nearest
+// edge pixel / row.
+__device__ __forceinline__ unsigned mword_shift_rep(const unsigned* M, const Geom& g, int y, int c, int dx) {
+    unsigned edge = dx < 0 ? (M[y * g.wpr] & 1u) : ((M[y * g.wpr + g.wpr - 1] >> ((g.w - 1) & 31)) & 1u);
+    return mword_shift(M, g, y, c, dx, edge ? 0xffffffffu : 0u);
+}
+
+// Centred square erosion by radius r with out-of-crop = 1
+// (cv2.erode(seg_bin, None, iterations=r), indexing_ui.py:1497).
+// Window doubling on 32-px words: with W_a[x] = AND of the in-crop pixels of
+// [x-a, x+a], W_{a+b}[x] = W_a[clamp(x-b)] & W_a[clamp(x+b)] for b <= a (clamping the
+// position keeps every term inside the target window), so any radius takes
+// ceil(log2 r)+1 passes per axis.  Ping-pongs between bufA and bufB; returns the
+// buffer that holds the result.  `src` must not be bufA or bufB's partner in use.
+__device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsigned* bufB, const Geom& g, int r) {
+    const unsigned* cur = src;
+    unsigned* nxt = (src == bufA) ? bufB : bufA;
+    int a = 0;
+    while (a < r) {                                    // horizontal
+        int b = (a == 0) ? 1 : ((2 * a <= r) ? a : (r - a));
+        for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+            int y = i / g.wpr, c = i - y * g.wpr;
+            unsigned v = mword_shift_rep(cur, g, y, c, -b) & mword_shift_rep(cur, g, y, c, +b);
+            if (a == 0) v &= cur[i];
+            nxt[i] = v & row_mask_of(g, c);
+        }
+        __syncthreads();
+        a += b;
+        cur = nxt;
+        nxt = (cur == bufA) ? bufB : bufA;
+    }
+    a = 0;
+    while (a < r) {                                    // vertical
+        int b = (a == 0) ? 1 : ((2 * a <= r) ? a : (r - a));
+        for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+            int y = i / g.wpr, c = i - y * g.wpr;
+            unsigned v = cur[max(y - b, 0) * g.wpr + c] & cur[min(y + b, g.h - 1) * g.wpr + c];
+            if (a == 0) v &= cur[i];
+            nxt[i] = v;
+        }
+        __syncthreads();
+        a += b;
+        cur = nxt;
+        nxt = (cur == bufA) ? bufB : bufA;
+    }
+    return const_cast<unsigned*>(cur);
+}
+
+__device__ inline unsigned cta_popcount(CtaScratch& cs, const unsigned* M, const Geom& g) {
+    unsigned long long n = 0;
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) n += __popc(M[i]);
+    return (unsigned)cta_sum_u64(cs, n);
+}
+
+}  // namespace vi

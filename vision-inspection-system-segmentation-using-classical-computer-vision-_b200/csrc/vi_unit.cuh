@@ -1,0 +1,355 @@
+// vi_unit.cuh -- process_unit(): one CTA runs every stage of one unit with the
+// crop and all masks resident in shared memory, and the persistent kernel that
+// strides units over the grid.
+#pragma once
+#include <cmath>
+#include "vi_pipeline.cuh"
+
+namespace vi {
+
+// Canonical (raster-order) label of every root: 1 + number of roots with a smaller
+// run id.  Stored in acc1[root]; returns the number of components.
+__device__ inline int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
+    unsigned carry = 0;
+    for (int base = 0; base < R; base += kThreads) {
+        int i = base + threadIdx.x + 1;
+        unsigned isroot = (i <= R && ws.parent[i] == i) ? 1u : 0u;
+        unsigned a = isroot, b = 0, ta, tb;
+        cta_excl_scan2(cs, a, b, ta, tb);
+        if (isroot) ws.acc1[i] = carry + a + 1;
+        carry += ta;
+    }
+    __syncthreads();
+    return (int)carry;
+}
+
+// int32 labels, unit-packed [h][w]: 0 background, else acc1[root].
+__device__ inline void store_labels(const Geom& g, const CclWs& ws, int32_t* __restrict__ dst) {
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+        int y = i / g.wpr, c = i - y * g.wpr;
+        int x0 = c * 32, x1 = min(x0 + 31, g.w - 1);
+        int j = ws.row_first[y], j1 = ws.row_first[y + 1];
+        while (j < j1 && (int)ws.xe[j] < x0) ++j;
+        for (int x = x0; x <= x1; ++x) {
+            while (j < j1 && (int)ws.xe[j] < x) ++j;
+            int lab = 0;
+            if (j < j1 && (int)ws.xs[j] <= x) lab = (int)ws.acc1[ws.parent[j]];
+            dst[(long long)y * g.w + x] = lab;
+        }
+    }
+}
+
+__device__ inline void zero_bytes(uint8_t* __restrict__ dst, int n) {
+    for (int e = threadIdx.x; e < n; e += kThreads) dst[e] = 0;
+}
+
+__device__ inline void select_levels(UnitShared& sh, int npix, int thr) {
+    // Six levels around the two Otsu class medians of the (blurred) histogram.
+    // Any level set is exact; these make the bracket decide nearly every pixel.
+    if (threadIdx.x == 0) {
+        const int t = sh.otsu_t;
+        unsigned nd = 0;
+        for (int v = 0; v <= t; ++v) nd += sh.hist[v];
+        unsigned nb = (unsigned)npix - nd;
+        int cd = t, cb = t;
+        unsigned acc = 0;
+        if (nd) { unsigned tgt = (nd + 1) / 2; for (int v = 0; v <= t; ++v) { acc += sh.hist[v]; if (acc >= tgt) { cd = v; break; } } }
+        acc = 0;
+        if (nb) { unsigned tgt = (nb + 1) / 2; for (int v = t + 1; v < 256; ++v) { acc += sh.hist[v]; if (acc >= tgt) { cb = v; break; } } }
+        int s = 1;
+        int lim = thr / 3 > 1 ? thr / 3 : 1;
+        while (s * 2 <= lim && s < 16) s *= 2;
+        int lv[kLevels] = {cd - s, cd, cd + s, cb - s, cb, cb + s};
+        for (int i = 0; i < kLevels; ++i) lv[i] = min(254, max(0, lv[i]));
+        for (int i = 1; i < kLevels; ++i) {
+            int v = lv[i], j = i - 1;
+            while (j >= 0 && lv[j] > v) { lv[j + 1] = lv[j]; --j; }
+            lv[j + 1] = v;
+        }
+        for (int i = 0; i < kLevels; ++i) sh.levels[i] = lv[i];
+    }
+    __syncthreads();
+}
+
+__device__ inline void write_record(const KArgs& a, int uid, int img, int unit, int otsu_t, unsigned seg_area,
+                                    unsigned roi_area, unsigned defect_area, int n_kept, int status, int dx, int dy,
+                                    double cx, double cy, int n_amb, int n_runs) {
+    if (threadIdx.x == 0 && a.rec) {
+        vi_unit_record r;
+        r.image = img; r.unit = unit; r.otsu_t = otsu_t; r.seg_area = (int)seg_area; r.roi_area = (int)roi_area;
+        r.defect_area = (int)defect_area; r.n_kept = n_kept; r.status = status; r.dx = dx; r.dy = dy;
+        r.cx = cx; r.cy = cy; r.n_ambiguous = n_amb; r.n_runs = n_runs;
+        a.rec[uid] = r;
+    }
+}
+
+__device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitShared& sh) {
+    const int tid = threadIdx.x;
+    const int img = uid / a.n_units, unit = uid - img * a.n_units;
+    const int4 rc = a.rects[unit];
+    const Geom g = make_geom(rc.z, rc.w);
+    const SmemPlan& plan = a.plan;
+    const int npix = g.w * g.h;
+    const int mode = a.mode;
+
+    uint8_t* gray = smem;
+    unsigned char* Rg = smem + plan.gray_bytes;
+    unsigned* MA = reinterpret_cast<unsigned*>(Rg + 0 * plan.mask_bytes);
+    unsigned* MB = reinterpret_cast<unsigned*>(Rg + 1 * plan.mask_bytes);
+    unsigned* MC = reinterpret_cast<unsigned*>(Rg + 2 * plan.mask_bytes);
+    unsigned* MD = reinterpret_cast<unsigned*>(Rg + 3 * plan.mask_bytes);
+    unsigned* ME = reinterpret_cast<unsigned*>(Rg + 4 * plan.mask_bytes);
+    unsigned char* WS = Rg + kNumMasks * plan.mask_bytes;
+
+    // per-CTA global scratch: [u16 hsum][u8 blurred][run-table overflow]
+    unsigned char* gs = a.scratch + (long long)blockIdx.x * a.scratch_stride;
+    const long long maxpx = (long long)a.wmax * a.hmax;
+    unsigned short* g_hp = reinterpret_cast<unsigned short*>(gs);
+    uint8_t* g_blur = gs + ((maxpx * 2 + 15) & ~15ll);
+    unsigned char* g_ccl = g_blur + ((maxpx + 15) & ~15ll);
+    const int capg = a.hmax * (a.wmax / 2 + 1);
+    const CclWs ws_s = ccl_ws_carve(WS, plan.run_cap, a.hmax);
+    const CclWs ws_g = ccl_ws_carve(g_ccl, capg, a.hmax);
+    CclWs ws;
+
+    const long long moff = (long long)img * a.unit_px + a.unit_off[unit];
+    uint8_t* seg_out = a.seg_out ? a.seg_out + moff : nullptr;
+    uint8_t* def_out = a.def_out ? a.def_out + moff : nullptr;
+    int32_t* lab_out = a.labels_out ? a.labels_out + moff : nullptr;
+    const uint8_t* aux = a.aux_mask ? a.aux_mask + moff : nullptr;
+    long long* stats = a.stats_out ? a.stats_out + (long long)uid * 8 : nullptr;
+
+    const bool need_gray = mode == MODE_FULL || mode == MODE_SEG_ONLY || mode == MODE_DETECT;
+    const bool need_seg = mode == MODE_FULL || mode == MODE_SEG_ONLY;
+    int otsu_t = 0, dx = 0, dy = 0, n_runs_max = 0;
+    double cx = __longlong_as_double(0x7ff8000000000000ll), cy = cx;
+    unsigned seg_area = 0;
+
+    if (need_gray) {
+        const uint8_t* src = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
+        load_gray(src, a.row_pitch, g, gray);
+        __syncthreads();
+        // ---- P1: blur + histogram ------------------------------------------------
+        const int src_mode = (mode == MODE_DETECT || a.blur_k == 0) ? 0 : (a.blur_k == 3 ? 1 : 2);
+        if (src_mode == 2) blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
+        unsigned* hist_base = reinterpret_cast<unsigned*>(Rg);
+        for (int i = tid; i < plan.n_hist * kHistWords; i += kThreads) hist_base[i] = 0;
+        if (tid < 256) sh.hist[tid] = 0;
+        __syncthreads();
+        for (int r0 = 0; r0 < kWarps; r0 += plan.n_hist) {
+            unsigned* hw = hist_base + (warp_id() - r0) * kHistWords;
+            if (src_mode == 0) blur_pass<0, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+            else if (src_mode == 1) blur_pass<1, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+            else blur_pass<2, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+            __syncthreads();
+        }
+        // ---- P2: Otsu ------------------------------------------------------------
+        OtsuWs ow;
+        ow.p = reinterpret_cast<double*>(WS);
+        ow.ip = ow.p + 256; ow.q1 = ow.ip + 256; ow.mu1 = ow.q1 + 256; ow.sig = ow.mu1 + 256;
+        otsu_t = otsu_scan(sh.cs, sh.hist, npix, ow);
+        if (tid == 0) sh.otsu_t = otsu_t;
+        __syncthreads();
+
+        if (need_seg) {
+            // ---- P3: inverse threshold ------------------------------------------
+            if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
+            else if (src_mode == 1) blur_pass<1, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
+            else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
+            __syncthreads();
+            // ---- P4: close, open --------------------------------------------------
+            if (a.se_k == 3) {
+                cross3_pass<false>(MA, MB, g); __syncthreads();
+                cross3_pass<true>(MB, MA, g); __syncthreads();
+                cross3_pass<true>(MA, MB, g); __syncthreads();
+                cross3_pass<false>(MB, MA, g); __syncthreads();
+            } else if (a.se_k > 0) {
+                se_pass<false>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
+                se_pass<true>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
+                se_pass<true>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
+                se_pass<false>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
+            }
+            // ---- P5: hole fill ----------------------------------------------------
+            for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i % g.wpr);
+            __syncthreads();
+            int R = ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws);
+            n_runs_max = max(n_runs_max, R);
+            ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
+            __syncthreads();
+            if (mode == MODE_FULL) {
+                // ---- P6: largest 8-component centroid, shift ---------------------
+                R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws);
+                n_runs_max = max(n_runs_max, R);
+                unsigned area; unsigned long long sx, sy;
+                int broot = ccl_largest(sh.cs, g, ws, R, area, sx, sy);
+                if (broot != 0 && area > 0) {
+                    cx = __ddiv_rn((double)sx, (double)area);
+                    cy = __ddiv_rn((double)sy, (double)area);
+                    if (!a.is_reference && a.refc) {
+                        double c0x = a.refc[2 * unit], c0y = a.refc[2 * unit + 1];
+                        if (c0x == c0x && c0y == c0y) {
+                            dx = __double2int_rn(__dsub_rn(cx, c0x));
+                            dy = __double2int_rn(__dsub_rn(cy, c0y));
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- P7: exclusions ------------------------------------------------
+                if (a.n_excl > 0) { apply_exclusions(MA, g, a.excl, a.n_excl, dx, dy); __syncthreads(); }
+            }
+            // ---- P8: seg mask out -------------------------------------------------
+            seg_area = cta_popcount(sh.cs, MA, g);
+            if (seg_out) store_mask_bytes(MA, g, seg_out);
+            if (mode == MODE_SEG_ONLY) {
+                write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, 0, 0, 0, cx, cy, 0, n_runs_max);
+                return;
+            }
+        }
+    }
+
+    if (mode == MODE_FILL || mode == MODE_STATS || mode == MODE_ERODE || mode == MODE_LABEL || mode == MODE_DETECT) {
+        load_mask_bits(aux, g, MA);
+        __syncthreads();
+    }
+    if (mode == MODE_FILL) {
+        for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i % g.wpr);
+        __syncthreads();
+        ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws);
+        ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
+        __syncthreads();
+        store_mask_bytes(MA, g, seg_out);
+        return;
+    }
+    if (mode == MODE_STATS) {
+        unsigned long long n = 0, sx = 0, sy = 0;
+        for (int i = tid; i < g.nwords; i += kThreads) {
+            int y = i / g.wpr, c = i - y * g.wpr;
+            unsigned m = MA[i];
+            unsigned pc = __popc(m);
+            unsigned pos = __popc(m & 0xAAAAAAAAu) + 2 * __popc(m & 0xCCCCCCCCu) + 4 * __popc(m & 0xF0F0F0F0u) +
+                           8 * __popc(m & 0xFF00FF00u) + 16 * __popc(m & 0xFFFF0000u);
+            n += pc; sx += (unsigned long long)pc * (c * 32) + pos; sy += (unsigned long long)pc * y;
+        }
+        n = cta_sum_u64(sh.cs, n); sx = cta_sum_u64(sh.cs, sx); sy = cta_sum_u64(sh.cs, sy);
+        if (tid == 0) { stats[0] = (long long)n; stats[1] = (long long)sx; stats[2] = (long long)sy; }
+        return;
+    }
+    if (mode == MODE_ERODE) {
+        unsigned* X = MA;
+        if (a.erode_r > 0) X = erode_square_bits(MA, MB, MC, g, a.erode_r);
+        store_mask_bytes(X, g, seg_out);
+        return;
+    }
+    if (mode == MODE_LABEL) {
+        int R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws);
+        unsigned area; unsigned long long sx, sy;
+        int broot = ccl_largest(sh.cs, g, ws, R, area, sx, sy);
+        int nlab = ccl_rank_roots(sh.cs, ws, R);
+        if (lab_out) store_labels(g, ws, lab_out);
+        if (tid == 0) {
+            stats[0] = nlab; stats[1] = broot ? (long long)ws.acc1[broot] : 0; stats[2] = area;
+            stats[3] = (long long)sx; stats[4] = (long long)sy; stats[5] = R;
+        }
+        return;
+    }
+    if (mode == MODE_DETECT) seg_area = cta_popcount(sh.cs, MA, g);
+
+    // =========================== detector ======================================
+    // ---- P9: square erosion ---------------------------------------------------
+    unsigned* X = MA;
+    if (a.p.erode_px > 0) X = erode_square_bits(MA, MB, MC, g, a.p.erode_px);
+    // ---- P10: largest 8-component = ROI ---------------------------------------
+    int R = ccl_build(sh.cs, X, g, true, false, ws_s, ws_g, ws);
+    n_runs_max = max(n_runs_max, R);
+    unsigned roi_area; unsigned long long rsx, rsy;
+    const int broot = ccl_largest(sh.cs, g, ws, R, roi_area, rsx, rsy);
+    if (lab_out) {
+        ccl_rank_roots(sh.cs, ws, R);
+        store_labels(g, ws, lab_out);
+    }
+    if (broot == 0 || roi_area == 0) {
+        if (def_out) zero_bytes(def_out, npix);
+        write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, VI_STATUS_ROI_EMPTY, dx, dy, cx, cy, 0, n_runs_max);
+        return;
+    }
+    ccl_paint(MD, nullptr, g, ws, [broot](int root) { return root == broot; });
+    __syncthreads();
+    // ---- P11: median residual -------------------------------------------------
+    const int thr = a.p.threshold;
+    RankWs rw;
+    rw.lut = reinterpret_cast<uint2*>(WS);
+    rw.dec = reinterpret_cast<unsigned short*>(WS + 256 * 8);
+    rw.band = reinterpret_cast<uint2*>(WS + 256 * 8 + 256 * 2);
+    select_levels(sh, npix, thr);
+    if (g.w <= kRankMaxW) {
+        rank_tables(sh.levels, thr, rw);
+        __syncthreads();
+        rank_stage_fast(gray, g, plan, rw, MA, MB);
+    } else {
+        for (int i = tid; i < g.nwords; i += kThreads) { MA[i] = 0; MB[i] = row_mask_of(g, i % g.wpr); }
+        __syncthreads();
+    }
+    for (int i = tid; i < g.nwords; i += kThreads) {
+        unsigned roi = MD[i];
+        MC[i] = MA[i] & roi;
+        MB[i] = MB[i] & ~MA[i] & roi;
+    }
+    __syncthreads();
+    unsigned n_amb = rank_exact(gray, g, thr, MC, MB);
+    n_amb = (unsigned)cta_sum_u64(sh.cs, n_amb);
+    // ---- P12: open with the 3x3 cross -----------------------------------------
+    cross3_pass<true>(MC, MA, g); __syncthreads();
+    cross3_pass<false>(MA, MB, g); __syncthreads();
+    // ---- P13: hole fill + per-component contour area filter ---------------------
+    for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i % g.wpr);
+    __syncthreads();
+    R = ccl_build(sh.cs, MC, g, false, true, ws_s, ws_g, ws);
+    n_runs_max = max(n_runs_max, R);
+    ccl_paint(MB, MB, g, ws, [](int root) { return root != 0; });
+    __syncthreads();
+    R = ccl_build(sh.cs, MB, g, true, false, ws_s, ws_g, ws);
+    n_runs_max = max(n_runs_max, R);
+    {
+        const int Rpad = (R + kThreads - 1) / kThreads * kThreads;
+        for (int base = 0; base < Rpad; base += kThreads) {
+            int i = base + tid + 1;
+            bool valid = i <= R;
+            int root = valid ? ws.parent[i] : 0;
+            unsigned a2 = valid ? run_quad_area2(MB, g, ws.yy[i], ws.xs[i], ws.xe[i]) : 0u;
+            agg_add(ws.acc0, valid, root, a2);
+        }
+    }
+    __syncthreads();
+    const long long min_area = a.p.min_area;
+    long long max_area = (long long)__double2ll_rz(__dmul_rn((double)roi_area, a.p.max_area_frac));
+    if (max_area < min_area) max_area = min_area;
+    const unsigned* acc0 = ws.acc0;
+    auto keep = [acc0, min_area, max_area](int root) {
+        long long a2 = acc0[root];
+        return a2 >= 2 * min_area && a2 <= 2 * max_area;
+    };
+    unsigned long long kept = 0;
+    for (int i = 1 + tid; i <= R; i += kThreads)
+        if (ws.parent[i] == i && keep(i)) ++kept;
+    const int n_kept = (int)cta_sum_u64(sh.cs, kept);
+    ccl_paint(ME, nullptr, g, ws, keep);
+    __syncthreads();
+    // ---- P14: verdict ---------------------------------------------------------
+    const unsigned defect_area = cta_popcount(sh.cs, ME, g);
+    if (def_out) store_mask_bytes(ME, g, def_out);
+    const int status = (n_kept > 0 && (long long)defect_area >= min_area) ? VI_STATUS_NG : VI_STATUS_OK;
+    write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, n_kept > 0 ? defect_area : 0u, n_kept, status, dx, dy,
+                 cx, cy, (int)n_amb, n_runs_max);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ UnitShared sh;
+    const int n_total = a.n_images * a.n_units;
+    for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
+        process_unit(a, uid, smem, sh);
+        __syncthreads();
+    }
+}
+
+}  // namespace vi
