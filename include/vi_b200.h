@@ -147,6 +147,14 @@ int vi_detect_defects(vi_ctx* ctx, const uint8_t* gray, const uint8_t* seg_mask,
                       const vi_params* params, uint8_t* out_mask, int32_t* found,
                       vi_unit_record* out_record_or_null);
 
+/* ---- diagnostics -------------------------------------------------------------- */
+/* Per-phase SM cycle counts of every unit of subsequent vi_inspect_batch calls:
+ * d_cycles is device memory, [n_images*n_units][32] int64 (NULL switches it off). */
+int vi_debug_set_profile(vi_ctx* ctx, long long* d_cycles);
+/* Compares the reciprocal-based division of the Otsu recurrence with the IEEE divide on
+ * n_samples pseudo-random operand pairs; *mismatches must come back 0. */
+int vi_debug_fastdiv_check(vi_ctx* ctx, long long n_samples, unsigned long long seed, long long* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,6 +260,16 @@ def test_host_batch_equals_device_batch(insp, golden):
             assert rec_h[fi * 48 + i]['status'] == recs[i]['status']
 
 
+def test_fast_division_is_ieee(insp):
+    """The Otsu recurrence divides through a precomputed reciprocal (two residual
+    corrections); it must be the correctly rounded quotient, bit for bit."""
+    import ctypes as C
+    from vi_b200 import _lib
+    bad = C.c_int64(-1)
+    _lib.check(insp._lib.vi_debug_fastdiv_check(insp._ctx, 1 << 28, 12345, C.byref(bad)))
+    assert bad.value == 0
+
+
 def test_error_paths(insp):
     from vi_b200 import segmentation as seg
     assert seg.fill_internal_holes(None) is None

@@ -35,7 +35,7 @@ EXPORTS = [
     "vi_last_error", "vi_version", "vi_params_default", "vi_ctx_create", "vi_ctx_destroy", "vi_set_grid",
     "vi_set_exclusions", "vi_set_ref_centroids", "vi_unit_pixels", "vi_unit_offsets", "vi_inspect_batch",
     "vi_inspect_batch_host", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
-    "vi_label_components", "vi_detect_defects",
+    "vi_label_components", "vi_detect_defects", "vi_debug_set_profile", "vi_debug_fastdiv_check",
 ]
 
 _lib = None
@@ -79,6 +79,8 @@ def load():
     lib.vi_mask_stats.argtypes = [vp, vp, C.c_int, C.c_int, P(i64), P(i64), P(i64)]
     lib.vi_erode_square.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.vi_label_components.argtypes = [vp, vp, C.c_int, C.c_int, vp, P(i32), P(i32), P(i64), P(i64), P(i64)]
+    lib.vi_debug_set_profile.argtypes = [vp, vp]
+    lib.vi_debug_fastdiv_check.argtypes = [vp, i64, C.c_uint64, P(i64)]
     lib.vi_detect_defects.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(ViParams), vp, P(i32), vp]
     for n in EXPORTS:
         f = getattr(lib, n)

@@ -74,6 +74,7 @@ struct vi_ctx {
     DevBuf hb_frames[2], hb_seg[2], hb_def[2], hb_rec[2];
     cudaStream_t streams[2] = {nullptr, nullptr};
     int smem_set = 0;
+    long long* prof = nullptr;
 };
 
 extern "C" const char* vi_last_error(void) { return g_err.c_str(); }
@@ -184,6 +185,55 @@ extern "C" int vi_set_ref_centroids(vi_ctx* c, const double* cxcy, int n_units, 
     return VI_OK;
 }
 
+// Diagnostics: div_by_rcp against the IEEE divide on pseudo-random operand pairs drawn like
+// the Otsu recurrence's (numerator in [0, 256), divisor in (2^-24, 1]), plus divisors with
+// long runs of one bits in the significand.
+__global__ void fastdiv_check_kernel(unsigned long long seed, long long per_thread, unsigned long long* bad) {
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned long long nbad = 0;
+    for (long long i = 0; i < per_thread; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long m1 = s & 0x000fffffffffffffull;
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long m2 = s & 0x000fffffffffffffull;
+        const int kind = (int)((s >> 52) & 7);
+        if (kind == 0) m2 |= 0x000fffffffff0000ull;                 // significand close to all ones
+        if (kind == 1) m2 = 0x000fffffffffffffull - (m2 & 0xff);
+        if (kind == 2) m1 &= 0x000ff00000000000ull;                 // short numerators (small integers / sums)
+        const int eb = 1023 - (int)((s >> 56) % 24);                // divisor in (2^-24, 1]
+        const int en = 1023 + 7 - (int)((s >> 60) % 12);            // numerator in [2^-4, 256)
+        const double b = __longlong_as_double(((long long)eb << 52) | (long long)m2);
+        const double n = __longlong_as_double(((long long)en << 52) | (long long)m1);
+        const double r = __ddiv_rn(1.0, b);
+        const double q = vi::div_by_rcp(n, b, r), ref = __ddiv_rn(n, b);
+        if (__double_as_longlong(q) != __double_as_longlong(ref)) ++nbad;
+    }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
+extern "C" int vi_debug_fastdiv_check(vi_ctx* c, long long n_samples, unsigned long long seed, long long* mismatches) {
+    if (!c || !mismatches) return fail(VI_ERR_ARG, "vi_debug_fastdiv_check: null");
+    CU(cudaSetDevice(c->device));
+    unsigned long long* d_bad = nullptr;
+    CU(cudaMalloc(&d_bad, 8));
+    CU(cudaMemset(d_bad, 0, 8));
+    const int blocks = 4 * c->sm_count, threads = 256;
+    long long per = (n_samples + (long long)blocks * threads - 1) / ((long long)blocks * threads);
+    fastdiv_check_kernel<<<blocks, threads>>>(seed, per, d_bad);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d_bad, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return fail(VI_ERR_CUDA, "fastdiv check: %s", cudaGetErrorString(e));
+    *mismatches = (long long)h;
+    return VI_OK;
+}
+
+extern "C" int vi_debug_set_profile(vi_ctx* c, long long* d_cycles) {
+    if (!c) return fail(VI_ERR_ARG, "ctx is null");
+    c->prof = d_cycles;
+    return VI_OK;
+}
+
 extern "C" int64_t vi_unit_pixels(vi_ctx* c) { return c ? c->grid.unit_px : 0; }
 
 extern "C" int vi_unit_offsets(vi_ctx* c, int64_t* out) {
@@ -289,6 +339,7 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     a.scratch_stride = c->scratch_stride;
     a.wmax = gs.wmax; a.hmax = gs.hmax;
     a.plan = gs.plan;
+    a.prof = (&gs == &c->grid) ? c->prof : nullptr;
     if (c->smem_set < gs.plan.total) {
         CU(cudaFuncSetAttribute(vi_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
         c->smem_set = c->smem_optin - c->smem_static;

@@ -91,7 +91,7 @@ __device__ __forceinline__ void run_edges(const unsigned* M, const Geom& g, int 
 // Builds runs + components of mask M.  ws_s (shared) is used when the runs fit,
 // else ws_g (global scratch).  Returns R (run count) and the workspace used.
 __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
-                                const CclWs& ws_s, const CclWs& ws_g, CclWs& ws) {
+                                const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PhaseTimer* pt = nullptr) {
     const int per = (g.nwords + kThreads - 1) / kThreads;
     const int i0 = threadIdx.x * per;
     const int i1 = min(i0 + per, g.nwords);
@@ -105,6 +105,7 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
     }
     unsigned os = ns, oe = ne, R, Re;
     cta_excl_scan2(cs, os, oe, R, Re);
+    if (pt) pt->acc(23);
     ws = ((int)R <= ws_s.cap) ? ws_s : ws_g;
     for (int i = i0; i < i1; ++i) {
         int y = i / g.wpr, c = i - y * g.wpr;
@@ -125,6 +126,7 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
     }
     if (threadIdx.x == 0) { ws.row_first[g.h] = (int)R + 1; ws.parent[0] = 0; ws.acc0[0] = 0; ws.acc1[0] = 0; }
     __syncthreads();
+    if (pt) pt->acc(24);
     const int c8 = conn8 ? 1 : 0;
     // A: primary link = first overlapping run of the row above
     for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
@@ -145,7 +147,9 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
         ws.acc1[i] = 0;
     }
     __syncthreads();
+    if (pt) pt->acc(25);
     ccl_jump(ws.parent, (int)R);
+    if (pt) pt->acc(26);
     // C: remaining overlaps and the border link
     for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
         int y = ws.yy[i];
@@ -162,7 +166,9 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
         if (border && (y == 0 || y == g.h - 1 || xs == 0 || xe == g.w - 1)) uf_unite(ws.parent, i, 0);
     }
     __syncthreads();
+    if (pt) pt->acc(27);
     ccl_jump(ws.parent, (int)R);
+    if (pt) pt->acc(28);
     return (int)R;
 }
 

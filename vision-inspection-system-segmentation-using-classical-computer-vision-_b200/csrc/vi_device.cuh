@@ -78,10 +78,11 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     Geom g = make_geom(wmax, hmax);
     p->gray_bytes = align16(g.gp * hmax);
     p->mask_bytes = align16(g.nwords * 4);
-    int nseg = (wmax + 20 + kSegL - 1) / kSegL;
-    if (nseg > 32) nseg = 32;
-    p->band_pitch = nseg * kSegL;
-    int band = kBandRows * p->band_pitch * 8 + 256 * 8 + 256 * 2 + 64;
+    p->band_pitch = 0;
+    // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
+    int nlx = (wmax + 2) / 3;
+    int csp = ((3 * nlx + 22 + kSegL - 1) / kSegL) * kSegL;
+    int band = csp <= 32 * kSegL ? 256 * 8 + 8 * ((wmax + 3) & ~3) * 4 + 16 * csp * 8 + 16 * ((nlx + 3) & ~3) * 4 + 64 : 0;
     int otsu = 256 * 8 * 5 + 256 * 4 + 256;
     int rowfirst = align16((hmax + 2) * 4);
     int want_cap = 2048;
@@ -136,6 +137,7 @@ struct KArgs {
     uint8_t* scratch;               // per-CTA global scratch (general blur path, run-table overflow)
     long long scratch_stride;
     int wmax, hmax;
+    long long* prof;                // diagnostics: [n_total][32] per-phase cycle counts, or null
     SmemPlan plan;
 };
 
@@ -150,6 +152,24 @@ struct CtaScratch {
     unsigned long long tot_l;
     int flag;
 };
+
+// Diagnostics: per-phase SM cycle counts of one unit (thread 0, after the barrier
+// that ends the phase), written only when KArgs::prof is set.
+constexpr int kProfSlots = 32;
+struct PhaseTimer {
+    long long* out;
+    long long t;
+    int k;
+    __device__ __forceinline__ void start(long long* o) { out = o; k = 0; if (out && threadIdx.x == 0) t = clock64(); }
+    __device__ __forceinline__ void tick() {
+        if (out && threadIdx.x == 0) { long long n = clock64(); if (k < kProfSlots) out[k] += n - t; ++k; t = n; }
+    }
+    // sub-phase accounting: add the time since the last tick/acc to `slot` without consuming a phase slot
+    __device__ __forceinline__ void acc(int slot) {
+        if (out && threadIdx.x == 0) { long long n = clock64(); out[slot] += n - t; t = n; }
+    }
+};
+
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
@@ -318,9 +338,39 @@ __device__ __forceinline__ unsigned mword_shift_rep(const unsigned* M, const Geo
 // position keeps every term inside the target window), so any radius takes
 // ceil(log2 r)+1 passes per axis.  Ping-pongs between bufA and bufB; returns the
 // buffer that holds the result.  `src` must not be bufA or bufB's partner in use.
+constexpr int kErodeDirectMax = 10;     // radii up to this take one direct pass per axis
+
 __device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsigned* bufB, const Geom& g, int r) {
     const unsigned* cur = src;
     unsigned* nxt = (src == bufA) ? bufB : bufA;
+    if (r <= kErodeDirectMax) {
+        // horizontal: AND of the 2r+1 shifts, built from the three neighbouring words (edge pixel replicated)
+        for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+            const int y = i / g.wpr, c = i - y * g.wpr;
+            const unsigned* row = cur + y * g.wpr;
+            const unsigned fl = (row[0] & 1u) ? 0xffffffffu : 0u;
+            const unsigned fr = ((row[g.wpr - 1] >> ((g.w - 1) & 31)) & 1u) ? 0xffffffffu : 0u;
+            const unsigned padr = fr & ~g.lastmask;
+            const unsigned C = row[c] | (c == g.wpr - 1 ? padr : 0u);
+            const unsigned L = c > 0 ? row[c - 1] : fl;
+            const unsigned R = c < g.wpr - 1 ? (row[c + 1] | (c + 1 == g.wpr - 1 ? padr : 0u)) : fr;
+            unsigned v = C;
+            for (int d = 1; d <= r; ++d) v &= __funnelshift_r(C, R, d) & __funnelshift_l(L, C, d);
+            nxt[i] = v & row_mask_of(g, c);
+        }
+        __syncthreads();
+        cur = nxt;
+        nxt = (cur == bufA) ? bufB : bufA;
+        // vertical: AND of the 2r+1 rows (edge row replicated)
+        for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+            const int y = i / g.wpr, c = i - y * g.wpr;
+            unsigned v = cur[i];
+            for (int d = 1; d <= r; ++d) v &= cur[max(y - d, 0) * g.wpr + c] & cur[min(y + d, g.h - 1) * g.wpr + c];
+            nxt[i] = v;
+        }
+        __syncthreads();
+        return nxt;
+    }
     int a = 0;
     while (a < r) {                                    // horizontal
         int b = (a == 0) ? 1 : ((2 * a <= r) ? a : (r - a));

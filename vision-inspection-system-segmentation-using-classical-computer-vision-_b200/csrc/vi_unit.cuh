@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include "vi_pipeline.cuh"
+#include "vi_rank.cuh"
 
 namespace vi {
 
@@ -45,28 +46,47 @@ __device__ inline void zero_bytes(uint8_t* __restrict__ dst, int n) {
 
 __device__ inline void select_levels(UnitShared& sh, int npix, int thr) {
     // Six levels around the two Otsu class medians of the (blurred) histogram.
-    // Any level set is exact; these make the bracket decide nearly every pixel.
-    if (threadIdx.x == 0) {
+    // Any level set is exact; these make the cell brackets decide nearly every pixel.
+    if (warp_id() == 0) {
+        const int lane = lane_id();
         const int t = sh.otsu_t;
-        unsigned nd = 0;
-        for (int v = 0; v <= t; ++v) nd += sh.hist[v];
-        unsigned nb = (unsigned)npix - nd;
-        int cd = t, cb = t;
-        unsigned acc = 0;
-        if (nd) { unsigned tgt = (nd + 1) / 2; for (int v = 0; v <= t; ++v) { acc += sh.hist[v]; if (acc >= tgt) { cd = v; break; } } }
-        acc = 0;
-        if (nb) { unsigned tgt = (nb + 1) / 2; for (int v = t + 1; v < 256; ++v) { acc += sh.hist[v]; if (acc >= tgt) { cb = v; break; } } }
-        int s = 1;
-        int lim = thr / 3 > 1 ? thr / 3 : 1;
-        while (s * 2 <= lim && s < 16) s *= 2;
-        int lv[kLevels] = {cd - s, cd, cd + s, cb - s, cb, cb + s};
-        for (int i = 0; i < kLevels; ++i) lv[i] = min(254, max(0, lv[i]));
-        for (int i = 1; i < kLevels; ++i) {
-            int v = lv[i], j = i - 1;
-            while (j >= 0 && lv[j] > v) { lv[j + 1] = lv[j]; --j; }
-            lv[j + 1] = v;
+        unsigned c[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tot += sh.hist[lane * 8 + k]; c[k] = tot; }      // inclusive within the lane
+        unsigned inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned x = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += x; }
+        const unsigned base = inc - tot;
+        // cumulative count at t (dark class size)
+        const unsigned at_t = __shfl_sync(kFull, base, t >> 3);
+        unsigned ct = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { unsigned v = __shfl_sync(kFull, c[k], t >> 3); if (k == (t & 7)) ct = v; }
+        const unsigned nd = at_t + ct, nb = (unsigned)npix - nd;
+        const unsigned tgt_d = (nd + 1) / 2, tgt_b = nd + (nb + 1) / 2;
+        // first bin whose cumulative count reaches the target
+        unsigned fd = 0xffffu, fb = 0xffffu;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            const unsigned cum = base + c[k];
+            if (nd && cum >= tgt_d) fd = lane * 8 + k;
+            if (nb && cum >= tgt_b) fb = lane * 8 + k;
         }
-        for (int i = 0; i < kLevels; ++i) sh.levels[i] = lv[i];
+        fd = __reduce_min_sync(kFull, fd);
+        fb = __reduce_min_sync(kFull, fb);
+        if (lane == 0) {
+            const int cd = nd ? (int)fd : t, cb = nb ? (int)fb : t;
+            int s = 1;
+            const int lim = thr / 3 > 1 ? thr / 3 : 1;
+            while (s * 2 <= lim && s < 16) s *= 2;
+            int l0 = cd - s, l1 = cd, l2 = cd + s, l3 = cb - s, l4 = cb, l5 = cb + s;
+            // cd <= t < cb, so only l2 / l3 can be out of order: a 2-element swap sorts the list
+            if (l2 > l3) { int x = l2; l2 = l3; l3 = x; }
+            if (l1 > l2) { int x = l1; l1 = l2; l2 = x; }
+            if (l3 > l4) { int x = l3; l3 = l4; l4 = x; }
+            sh.levels[0] = min(254, max(0, l0)); sh.levels[1] = min(254, max(0, l1)); sh.levels[2] = min(254, max(0, l2));
+            sh.levels[3] = min(254, max(0, l3)); sh.levels[4] = min(254, max(0, l4)); sh.levels[5] = min(254, max(0, l5));
+        }
     }
     __syncthreads();
 }
@@ -119,6 +139,8 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     const uint8_t* aux = a.aux_mask ? a.aux_mask + moff : nullptr;
     long long* stats = a.stats_out ? a.stats_out + (long long)uid * 8 : nullptr;
 
+    PhaseTimer pt;
+    pt.start(a.prof ? a.prof + (long long)uid * kProfSlots : nullptr);
     const bool need_gray = mode == MODE_FULL || mode == MODE_SEG_ONLY || mode == MODE_DETECT;
     const bool need_seg = mode == MODE_FULL || mode == MODE_SEG_ONLY;
     int otsu_t = 0, dx = 0, dy = 0, n_runs_max = 0;
@@ -129,6 +151,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         const uint8_t* src = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
         load_gray(src, a.row_pitch, g, gray);
         __syncthreads();
+        pt.tick();   // 0 gather
         // ---- P1: blur + histogram ------------------------------------------------
         const int src_mode = (mode == MODE_DETECT || a.blur_k == 0) ? 0 : (a.blur_k == 3 ? 1 : 2);
         if (src_mode == 2) blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
@@ -136,27 +159,42 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         for (int i = tid; i < plan.n_hist * kHistWords; i += kThreads) hist_base[i] = 0;
         if (tid < 256) sh.hist[tid] = 0;
         __syncthreads();
-        for (int r0 = 0; r0 < kWarps; r0 += plan.n_hist) {
-            unsigned* hw = hist_base + (warp_id() - r0) * kHistWords;
-            if (src_mode == 0) blur_pass<0, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
-            else if (src_mode == 1) blur_pass<1, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
-            else blur_pass<2, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+        if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
+            // default path: one histogram round on min(16, n_hist) warps
+            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0);
             __syncthreads();
+            hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
+            __syncthreads();
+        } else {
+            for (int r0 = 0; r0 < kWarps; r0 += plan.n_hist) {
+                unsigned* hw = hist_base + (warp_id() - r0) * kHistWords;
+                if (src_mode == 0) blur_pass<0, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+                else if (src_mode == 1) blur_pass<1, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+                else blur_pass<2, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
+                __syncthreads();
+                hist_collect(hist_base, min(plan.n_hist, kWarps - r0), sh.hist, true);
+                __syncthreads();
+            }
         }
+        pt.tick();   // 1 blur + histogram
         // ---- P2: Otsu ------------------------------------------------------------
         OtsuWs ow;
         ow.p = reinterpret_cast<double*>(WS);
-        ow.ip = ow.p + 256; ow.q1 = ow.ip + 256; ow.mu1 = ow.q1 + 256; ow.sig = ow.mu1 + 256;
+        ow.ip = ow.p + 256; ow.q1 = ow.ip + 256; ow.r = ow.q1 + 256; ow.mu1 = ow.r + 256;
+        ow.key = reinterpret_cast<unsigned long long*>(ow.mu1 + 256);
+        ow.nz = reinterpret_cast<unsigned*>(ow.key + 256);
         otsu_t = otsu_scan(sh.cs, sh.hist, npix, ow);
         if (tid == 0) sh.otsu_t = otsu_t;
         __syncthreads();
+        pt.tick();   // 2 otsu
 
         if (need_seg) {
             // ---- P3: inverse threshold ------------------------------------------
             if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
-            else if (src_mode == 1) blur_pass<1, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
+            else if (src_mode == 1) blur3_pass<false>(gray, g, nullptr, nullptr, kWarps, MA, otsu_t);
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             __syncthreads();
+            pt.tick();   // 3 threshold
             // ---- P4: close, open --------------------------------------------------
             if (a.se_k == 3) {
                 cross3_pass<false>(MA, MB, g); __syncthreads();
@@ -169,16 +207,18 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
                 se_pass<true>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
                 se_pass<false>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
             }
+            pt.tick();   // 4 close/open
             // ---- P5: hole fill ----------------------------------------------------
             for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i % g.wpr);
             __syncthreads();
-            int R = ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws);
+            int R = ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
             n_runs_max = max(n_runs_max, R);
             ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
             __syncthreads();
+            pt.tick();   // 5 hole fill
             if (mode == MODE_FULL) {
                 // ---- P6: largest 8-component centroid, shift ---------------------
-                R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws);
+                R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws, &pt);
                 n_runs_max = max(n_runs_max, R);
                 unsigned area; unsigned long long sx, sy;
                 int broot = ccl_largest(sh.cs, g, ws, R, area, sx, sy);
@@ -194,12 +234,14 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
                     }
                 }
                 __syncthreads();
+                pt.tick();   // 6 centroid labelling
                 // ---- P7: exclusions ------------------------------------------------
                 if (a.n_excl > 0) { apply_exclusions(MA, g, a.excl, a.n_excl, dx, dy); __syncthreads(); }
             }
             // ---- P8: seg mask out -------------------------------------------------
             seg_area = cta_popcount(sh.cs, MA, g);
             if (seg_out) store_mask_bytes(MA, g, seg_out);
+            pt.tick();   // 7 exclusions + seg mask out
             if (mode == MODE_SEG_ONLY) {
                 write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, 0, 0, 0, cx, cy, 0, n_runs_max);
                 return;
@@ -214,7 +256,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     if (mode == MODE_FILL) {
         for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i % g.wpr);
         __syncthreads();
-        ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws);
+        ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
         ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
         __syncthreads();
         store_mask_bytes(MA, g, seg_out);
@@ -241,7 +283,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         return;
     }
     if (mode == MODE_LABEL) {
-        int R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws);
+        int R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws, &pt);
         unsigned area; unsigned long long sx, sy;
         int broot = ccl_largest(sh.cs, g, ws, R, area, sx, sy);
         int nlab = ccl_rank_roots(sh.cs, ws, R);
@@ -258,8 +300,9 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     // ---- P9: square erosion ---------------------------------------------------
     unsigned* X = MA;
     if (a.p.erode_px > 0) X = erode_square_bits(MA, MB, MC, g, a.p.erode_px);
+    pt.tick();   // 8 erosion
     // ---- P10: largest 8-component = ROI ---------------------------------------
-    int R = ccl_build(sh.cs, X, g, true, false, ws_s, ws_g, ws);
+    int R = ccl_build(sh.cs, X, g, true, false, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     unsigned roi_area; unsigned long long rsx, rsy;
     const int broot = ccl_largest(sh.cs, g, ws, R, roi_area, rsx, rsy);
@@ -274,20 +317,22 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     }
     ccl_paint(MD, nullptr, g, ws, [broot](int root) { return root == broot; });
     __syncthreads();
+    pt.tick();   // 9 ROI labelling
     // ---- P11: median residual -------------------------------------------------
     const int thr = a.p.threshold;
-    RankWs rw;
-    rw.lut = reinterpret_cast<uint2*>(WS);
-    rw.dec = reinterpret_cast<unsigned short*>(WS + 256 * 8);
-    rw.band = reinterpret_cast<uint2*>(WS + 256 * 8 + 256 * 2);
     select_levels(sh, npix, thr);
-    if (g.w <= kRankMaxW) {
-        rank_tables(sh.levels, thr, rw);
+    if (rank_cs_pitch(g.w) <= 32 * kSegL && rank_ws_bytes(g.w) <= plan.ws_bytes) {
+        RankWs rw = rank_ws_carve(WS, g.w);
+        rank_tables(sh.levels, rw);
         __syncthreads();
-        rank_stage_fast(gray, g, plan, rw, MA, MB);
+        pt.tick();   // 10 levels + tables
+        rank_stage_lattice(gray, g, rw, sh.levels, thr, MA, MB, pt);
+        pt.tick();   // 11 rank counts
     } else {
         for (int i = tid; i < g.nwords; i += kThreads) { MA[i] = 0; MB[i] = row_mask_of(g, i % g.wpr); }
         __syncthreads();
+        pt.tick();
+        pt.tick();
     }
     for (int i = tid; i < g.nwords; i += kThreads) {
         unsigned roi = MD[i];
@@ -295,19 +340,21 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         MB[i] = MB[i] & ~MA[i] & roi;
     }
     __syncthreads();
-    unsigned n_amb = rank_exact(gray, g, thr, MC, MB);
-    n_amb = (unsigned)cta_sum_u64(sh.cs, n_amb);
+    unsigned n_amb = rank_exact_list(sh.cs, gray, g, thr, MC, MB, reinterpret_cast<unsigned*>(WS), plan.ws_bytes / 4);
+    pt.tick();   // 12 combine + exact rank counts
     // ---- P12: open with the 3x3 cross -----------------------------------------
     cross3_pass<true>(MC, MA, g); __syncthreads();
     cross3_pass<false>(MA, MB, g); __syncthreads();
+    pt.tick();   // 13 open
     // ---- P13: hole fill + per-component contour area filter ---------------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i % g.wpr);
     __syncthreads();
-    R = ccl_build(sh.cs, MC, g, false, true, ws_s, ws_g, ws);
+    R = ccl_build(sh.cs, MC, g, false, true, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     ccl_paint(MB, MB, g, ws, [](int root) { return root != 0; });
     __syncthreads();
-    R = ccl_build(sh.cs, MB, g, true, false, ws_s, ws_g, ws);
+    pt.tick();   // 14 defect hole fill
+    R = ccl_build(sh.cs, MB, g, true, false, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     {
         const int Rpad = (R + kThreads - 1) / kThreads * kThreads;
@@ -334,12 +381,14 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     const int n_kept = (int)cta_sum_u64(sh.cs, kept);
     ccl_paint(ME, nullptr, g, ws, keep);
     __syncthreads();
+    pt.tick();   // 15 component area filter
     // ---- P14: verdict ---------------------------------------------------------
     const unsigned defect_area = cta_popcount(sh.cs, ME, g);
     if (def_out) store_mask_bytes(ME, g, def_out);
     const int status = (n_kept > 0 && (long long)defect_area >= min_area) ? VI_STATUS_NG : VI_STATUS_OK;
     write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, n_kept > 0 ? defect_area : 0u, n_kept, status, dx, dy,
                  cx, cy, (int)n_amb, n_runs_max);
+    pt.tick();   // 16 defect mask out + record
 }
 
 __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
