@@ -80,10 +80,9 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     p->mask_bytes = align16(g.nwords * 4);
     p->band_pitch = 0;
     // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
-    int nlx = (wmax + 2) / 3;
-    int csp = ((3 * nlx + 22 + kSegL - 1) / kSegL) * kSegL;
-    int band = csp <= 32 * kSegL ? 256 * 8 + 8 * ((wmax + 3) & ~3) * 4 + 16 * csp * 8 + 16 * ((nlx + 3) & ~3) * 4 + 64 : 0;
-    int otsu = 256 * 8 * 5 + 256 * 4 + 256;
+    int rpitch = (wmax + 3) & ~3;
+    int band = wmax <= kThreads ? 2 * 256 * 4 + 8 * rpitch * 4 + 16 * rpitch * 8 + 64 : 0;
+    int otsu = 256 * 8 * 6 + 256;
     int rowfirst = align16((hmax + 2) * 4);
     int want_cap = 2048;
     int ccl = rowfirst + (want_cap + 1) * 18 + 64;

@@ -14,17 +14,19 @@
 //    of the cell   C_k >= 221 if C_k(centre) >= 263   and   C_k <= 220 if
 //    C_k(centre) <= 178,   which brackets the median of every pixel of the cell:
 //    LO < med <= HI with LO, HI taken from the level list (or -1 / 255).
-// 3. Per pixel, four byte thresholds of its cell decide: defect for sure
-//    (g <= LO-thr or g >= HI+thr+1), clean for sure (HI-thr <= g <= LO+thr+1), else
-//    "ambiguous": those pixels (inside the ROI) get an exact rank count at their own
-//    two pivots.  Exact for any level set and any image
+// 3. Four byte thresholds per cell decide a pixel: defect for sure (g <= LO-thr or
+//    g >= HI+thr+1), clean for sure (HI-thr <= g <= LO+thr+1), else "ambiguous".
+//    A cell whose 9 pixels' min and max are both in the clean range is finished
+//    (nearly all are); the few "dirty" cells are listed and classified per pixel,
+//    and ambiguous ROI pixels get an exact rank count at their own two pivots.
+//    Exact for any level set and any image
 //    (oracle/restate.py: residual_mask_lattice is the numpy twin).
 //
 // Box sums are separable.  V: one thread per column accumulates 3-row block sums
-// (a lattice row's 21-row window is exactly 7 blocks), a ring of packed block sums
-// gives the sliding 7-block sum.  H: one warp per lattice row turns the column
-// sums (10 replicated columns each side) into a prefix in place; a cell's window
-// sum is P[3i+21] - P[3i].
+// (a lattice row's 21-row window is exactly 7 blocks); a ring of packed block sums
+// gives the sliding 7-block sum.  H: one warp per lattice row, one lane per cell:
+// 3-column triple sums (10 replicated columns each side), a warp scan, and the
+// cell's 21-column window is P[i+6] - P[i-1].
 #pragma once
 #include "vi_device.cuh"
 
@@ -32,34 +34,40 @@ namespace vi {
 
 constexpr int kCell = 3;
 constexpr int kLatBand = 16;             // lattice rows per band (= warps per CTA)
+constexpr int kCellsPerPass = 26;        // 32 triples per pass, 6 of them look-ahead
 constexpr unsigned kFld = 0x00300C03u;   // 2-bit block-sum fields at the 10-bit field positions
 constexpr unsigned kFlag = 0x20080200u;  // bit 9 of each 10-bit field
 constexpr unsigned kGe263 = 249u | (249u << 10) | (249u << 20);   // field + 249 >= 512  <=>  field >= 263
 constexpr unsigned kGe179 = 333u | (333u << 10) | (333u << 20);   // field + 333 >= 512  <=>  field >= 179
 
 struct RankWs {
-    uint2* lut;         // [256] packed indicators of a gray value
-    unsigned* ring;     // [8][ring_pitch] packed 3-row block sums
-    uint2* cs;          // [kLatBand][cs_pitch] column sums, then prefix sums over the replicate-extended row
-    unsigned* cell;     // [kLatBand][cell_pitch] U1 | U2<<8 | U3<<16 | U4<<24
-    int ring_pitch, cs_pitch, cell_pitch;
+    unsigned* lut0;     // [256] indicators of levels 0..2 (10-bit fields)
+    unsigned* lut1;     // [256] indicators of levels 3..5
+    unsigned* ring;     // [8][pitch] packed 3-row block sums
+    uint2* cs;          // [kLatBand][pitch] 7-block column sums
+    uint2* dirty;       // [dirty_cap] (cell position, thresholds); more are classified inline
+    unsigned* exact;    // [exact_cap] ambiguous pixels (y << 16 | x); more are counted inline
+    int dirty_cap, exact_cap;
+    int* counters;      // [0] dirty cells, [1] ambiguous pixels listed, [2] ambiguous pixels total
+    int pitch;
 };
 
-__host__ __device__ inline int rank_nlx(int w) { return (w + kCell - 1) / kCell; }
-__host__ __device__ inline int rank_cs_pitch(int w) { return ((kCell * rank_nlx(w) + 22 + kSegL - 1) / kSegL) * kSegL; }
 __host__ __device__ inline int rank_ws_bytes(int w) {
-    return 256 * 8 + 8 * ((w + 3) & ~3) * 4 + kLatBand * rank_cs_pitch(w) * 8 + kLatBand * ((rank_nlx(w) + 3) & ~3) * 4 + 64;
+    const int pitch = (w + 3) & ~3;
+    return 2 * 256 * 4 + 8 * pitch * 4 + kLatBand * pitch * 8 + 64;
 }
 
-__device__ inline RankWs rank_ws_carve(unsigned char* base, int w) {
+// The two lists live in two mask buffers that are idle during this stage.
+__device__ inline RankWs rank_ws_carve(unsigned char* base, int w, unsigned* listA, unsigned* listB, int mask_bytes) {
     RankWs r;
-    r.ring_pitch = (w + 3) & ~3;
-    r.cs_pitch = rank_cs_pitch(w);
-    r.cell_pitch = (rank_nlx(w) + 3) & ~3;
-    r.lut = reinterpret_cast<uint2*>(base); base += 256 * 8;
-    r.cs = reinterpret_cast<uint2*>(base); base += kLatBand * r.cs_pitch * 8;
-    r.cell = reinterpret_cast<unsigned*>(base); base += kLatBand * r.cell_pitch * 4;
-    r.ring = reinterpret_cast<unsigned*>(base);
+    r.pitch = (w + 3) & ~3;
+    r.cs = reinterpret_cast<uint2*>(base); base += kLatBand * r.pitch * 8;
+    r.dirty = reinterpret_cast<uint2*>(listA); r.dirty_cap = mask_bytes / 8;
+    r.exact = listB; r.exact_cap = mask_bytes / 4;
+    r.lut0 = reinterpret_cast<unsigned*>(base); base += 256 * 4;
+    r.lut1 = reinterpret_cast<unsigned*>(base); base += 256 * 4;
+    r.ring = reinterpret_cast<unsigned*>(base); base += 8 * r.pitch * 4;
+    r.counters = reinterpret_cast<int*>(base);
     return r;
 }
 
@@ -69,30 +77,77 @@ __device__ inline void rank_tables(const int* lv, RankWs w) {
         unsigned lo = 0, hi = 0;
         for (int k = 0; k < 3; ++k) lo |= (unsigned)(v <= lv[k]) << (10 * k);
         for (int k = 0; k < 3; ++k) hi |= (unsigned)(v <= lv[3 + k]) << (10 * k);
-        w.lut[v] = make_uint2(lo, hi);
+        w.lut0[v] = lo;
+        w.lut1[v] = hi;
+    }
+    if (v < 4) w.counters[v] = 0;
+}
+
+// Exact decision for one pixel: #(window <= g+thr) <= 220 or #(window <= g-thr-1) >= 221.
+__device__ inline bool rank_exact_pixel_thread(const uint8_t* gray, const Geom& g, int thr, int x, int y) {
+    const int gv = gray[y * g.gp + x];
+    const int pa = gv + thr, pb = gv - thr - 1;
+    int ca = 0, cb = 0;
+    for (int dy = -10; dy <= 10; ++dy) {
+        const uint8_t* row = gray + min(max(y + dy, 0), g.h - 1) * g.gp;
+        for (int dx = -10; dx <= 10; ++dx) {
+            const int v = row[min(max(x + dx, 0), g.w - 1)];
+            ca += v <= pa;
+            cb += v <= pb;
+        }
+    }
+    return ca <= 220 || cb >= 221;
+}
+
+// Per-pixel classification of one dirty cell (one thread): defect-for-sure pixels of
+// the ROI go straight into CAND, ambiguous ones onto the exact list.
+__device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int thr, const unsigned* ROI, unsigned* CAND,
+                                       RankWs& w, int ci, int cj, unsigned cw) {
+    const unsigned u1 = cw & 255u, u2 = (cw >> 8) & 255u, u3 = (cw >> 16) & 255u, u4 = cw >> 24;
+    for (int rr = 0; rr < kCell; ++rr) {
+        const int y = cj * kCell + rr;
+        if (y >= g.h) break;
+        for (int cc = 0; cc < kCell; ++cc) {
+            const int x = ci * kCell + cc;
+            if (x >= g.w) break;
+            const int wi = y * g.wpr + (x >> 5);
+            const unsigned bit = 1u << (x & 31);
+            if (!(ROI[wi] & bit)) continue;
+            const unsigned gv = gray[y * g.gp + x];
+            if (gv < u1 || gv > u4) {
+                atomicOr(&CAND[wi], bit);
+            } else if (!(gv >= u2 && gv <= u3)) {
+                atomicAdd(&w.counters[2], 1);
+                const int k = atomicAdd(&w.counters[1], 1);
+                if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | (unsigned)x;
+                else if (rank_exact_pixel_thread(gray, g, thr, x, y)) atomicOr(&CAND[wi], bit);
+            }
+        }
     }
 }
 
-// SURE / AMB: per-pixel bit masks for the whole unit (all pixels, ROI or not).
-__device__ inline void rank_stage_lattice(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, int thr,
-                                          unsigned* SURE, unsigned* AMB, PhaseTimer& pt) {
+// CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
+// Returns the number of pixels that needed an exact rank count.
+__device__ inline int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom& g, RankWs w, const int* lv,
+                                         int thr, const unsigned* ROI, unsigned* CAND, PhaseTimer& pt) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    const int nly = (g.h + kCell - 1) / kCell, nlx = rank_nlx(g.w);
-    const int nseg = w.cs_pitch / kSegL;            // <= 32
+    const int nly = (g.h + kCell - 1) / kCell, nlx = (g.w + kCell - 1) / kCell;
+    const int ntrip = nlx + 6;
+    const int wm1 = g.w - 1, hm1 = g.h - 1;
     const bool vact = tid < g.w;
     const int vx = vact ? tid : 0;
     const uint8_t* gcol = gray + vx;
-    const int hm1 = g.h - 1;
     unsigned S0 = 0, S1 = 0;
     int b = -3;                                     // next 3-row block of this column
-    // gray bytes of block b, loaded one block ahead so the LUT loads never wait on them
+    // gray bytes of block b, loaded one block ahead so the table loads never wait on them
     unsigned q0 = gcol[0], q1 = q0, q2 = q0;
     for (int j0 = 0; j0 < nly; j0 += kLatBand) {
         const int j1 = min(j0 + kLatBand, nly);
         // ---- V: this column's blocks up to j1+2 ------------------------------------
         if (vact) {
             for (; b < j1 + 3; ++b) {
-                const uint2 e0 = w.lut[q0], e1 = w.lut[q1], e2 = w.lut[q2];
+                const unsigned B0 = w.lut0[q0] + w.lut0[q1] + w.lut0[q2];
+                const unsigned B1 = w.lut1[q0] + w.lut1[q1] + w.lut1[q2];
                 const int rn = kCell * (b + 1);
                 if (rn >= 0 && rn + 2 <= hm1) {                 // interior block: no clamping
                     const uint8_t* pr = gcol + rn * g.gp;
@@ -102,155 +157,118 @@ __device__ inline void rank_stage_lattice(const uint8_t* gray, const Geom& g, Ra
                     q1 = gcol[min(max(rn + 1, 0), hm1) * g.gp];
                     q2 = gcol[min(max(rn + 2, 0), hm1) * g.gp];
                 }
-                const unsigned o = w.ring[((b + 1) & 7) * w.ring_pitch + vx];
-                const unsigned B0 = e0.x + e1.x + e2.x, B1 = e0.y + e1.y + e2.y;
+                const unsigned o = w.ring[((b + 1) & 7) * w.pitch + vx];
                 S0 += B0; S1 += B1;
                 if (b >= 4) { S0 -= o & kFld; S1 -= (o >> 2) & kFld; }
-                w.ring[(b & 7) * w.ring_pitch + vx] = B0 | (B1 << 2);
-                if (b >= 3) w.cs[(b - 3 - j0) * w.cs_pitch + vx] = make_uint2(S0, S1);
+                w.ring[(b & 7) * w.pitch + vx] = B0 | (B1 << 2);
+                if (b >= 3) w.cs[(b - 3 - j0) * w.pitch + vx] = make_uint2(S0, S1);
             }
         }
         __syncthreads();
         pt.acc(20);
-        // ---- H: one warp per lattice row: prefix over the replicate-extended row ---
+        // ---- H: one warp per lattice row, one lane per cell --------------------------
         for (int jj = warp; jj < j1 - j0; jj += kWarps) {
-            uint2* row = w.cs + jj * w.cs_pitch;
-            const bool sact = lane < nseg;
-            unsigned p0[kSegL], p1[kSegL];
-            unsigned a0 = 0, a1 = 0;
-#pragma unroll
-            for (int t = 0; t < kSegL; ++t) {
-                // extended index e = 11*lane + t  <->  column clamp(e - 10)
-                int col = min(max(lane * kSegL + t - 10, 0), g.w - 1);
-                uint2 v = sact ? row[col] : make_uint2(0u, 0u);
-                a0 += v.x; a1 += v.y;
-                p0[t] = a0; p1[t] = a1;
-            }
-            unsigned t0 = a0, t1 = a1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned x0 = __shfl_up_sync(kFull, t0, o);
-                unsigned x1 = __shfl_up_sync(kFull, t1, o);
-                if (lane >= o) { t0 += x0; t1 += x1; }
-            }
-            const unsigned off0 = t0 - a0, off1 = t1 - a1;
-            __syncwarp();                            // every lane has read its columns before anyone overwrites
-            if (sact) {
-#pragma unroll
-                for (int t = 0; t < kSegL; ++t) row[lane * kSegL + t] = make_uint2(p0[t] + off0, p1[t] + off1);
-            }
-            __syncwarp();
-            for (int i = lane; i < nlx; i += 32) {
-                uint2 hi = row[kCell * i + 21], lo = row[kCell * i];
-                unsigned C0 = hi.x - lo.x, C1 = hi.y - lo.y;
-                int n263 = __popc((C0 + kGe263) & kFlag) + __popc((C1 + kGe263) & kFlag);
-                int n179 = __popc((C0 + kGe179) & kFlag) + __popc((C1 + kGe179) & kFlag);
-                int lo_idx = kLevels - n179;        // levels 0..lo_idx-1 surely have C <= 220: med >  LO
-                int hi_idx = kLevels - n263;        // level hi_idx surely has C >= 221:        med <= HI
-                int LO = lo_idx > 0 ? lv[lo_idx - 1] : -1;
-                int HI = hi_idx < kLevels ? lv[hi_idx] : 255;
-                int U1 = min(max(LO - thr + 1, 0), 255);     // defect if g <  U1
-                int U4 = min(HI + thr, 255);                 // defect if g >  U4
-                int U2 = max(HI - thr, 0);                   // clean needs g >= U2
-                int U3 = min(LO + thr + 1, 255);             // clean needs g <= U3
-                w.cell[jj * w.cell_pitch + i] = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
-            }
-        }
-        __syncthreads();
-        pt.acc(21);
-        // ---- classify: one warp per lattice row = three pixel rows sharing the cell words
-        for (int jj = warp; jj < j1 - j0; jj += kWarps) {
-            const unsigned* crow = w.cell + jj * w.cell_pitch;
-            const int yb = (j0 + jj) * kCell;
-            for (int c0 = 0; c0 < g.wpr; c0 += 5) {
-                unsigned gv[kCell][5], cE[5], cO[5];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const int x = min((c0 + k) * 32 + lane, g.w - 1);
-                    const unsigned cw = crow[x / kCell];
-                    cE[k] = __byte_perm(cw, 0u, 0x4240);          // (U1, U3)
-                    cO[k] = __byte_perm(cw, 0u, 0x4341);          // (U2, U4)
-#pragma unroll
-                    for (int rr = 0; rr < kCell; ++rr) gv[rr][k] = gray[min(yb + rr, hm1) * g.gp + x];
+            const uint2* row = w.cs + jj * w.pitch;
+            const int cj = j0 + jj;
+            for (int k0 = 0; k0 < nlx; k0 += kCellsPerPass) {
+                // triple k covers extended columns 3k+1..3k+3  <->  columns clamp(3k-9 .. 3k-7)
+                const int k = k0 + lane;
+                unsigned t0 = 0, t1 = 0;
+                if (k < ntrip) {
+                    const int c0 = kCell * k - 9;
+                    const uint2 a = row[min(max(c0, 0), wm1)], bb = row[min(max(c0 + 1, 0), wm1)],
+                                c = row[min(max(c0 + 2, 0), wm1)];
+                    t0 = a.x + bb.x + c.x; t1 = a.y + bb.y + c.y;
                 }
+                unsigned p0 = t0, p1 = t1;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const int c = c0 + k;
-                    if (c < g.wpr) {
-                        const bool act = c * 32 + lane < g.w;
-#pragma unroll
-                        for (int rr = 0; rr < kCell; ++rr) {
-                            if (yb + rr <= hm1) {
-                                // per 16-bit field: (g + 0x200) - U has bit 9 set iff g >= U, (g + 0x1FF) - U iff g > U
-                                const unsigned G2 = gv[rr][k] * 0x00010001u + 0x01FF0200u;
-                                const unsigned dE = G2 - cE[k], dO = G2 - cO[k];
-                                const bool ge1 = dE & 0x00000200u, gt3 = dE & 0x02000000u;
-                                const bool ge2 = dO & 0x00000200u, gt4 = dO & 0x02000000u;
-                                const bool df = !ge1 || gt4, ok = ge2 && !gt3;
-                                const unsigned sure = __ballot_sync(kFull, act && df);
-                                const unsigned amb = __ballot_sync(kFull, act && !df && !ok);
-                                if (lane == 0) { SURE[(yb + rr) * g.wpr + c] = sure; AMB[(yb + rr) * g.wpr + c] = amb; }
-                            }
-                        }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned x0 = __shfl_up_sync(kFull, p0, o), x1 = __shfl_up_sync(kFull, p1, o);
+                    if (lane >= o) { p0 += x0; p1 += x1; }
+                }
+                // window of cell i = k: triples i..i+6 = P[lane+6] - P[lane-1]
+                const unsigned h0 = __shfl_down_sync(kFull, p0, 6), h1 = __shfl_down_sync(kFull, p1, 6);
+                unsigned l0 = __shfl_up_sync(kFull, p0, 1), l1 = __shfl_up_sync(kFull, p1, 1);
+                if (lane == 0) { l0 = 0; l1 = 0; }
+                const bool cact = lane < kCellsPerPass && k < nlx;
+                bool dirty = false;
+                unsigned cw = 0;
+                if (cact) {
+                    const unsigned C0 = h0 - l0, C1 = h1 - l1;
+                    const int n263 = __popc((C0 + kGe263) & kFlag) + __popc((C1 + kGe263) & kFlag);
+                    const int n179 = __popc((C0 + kGe179) & kFlag) + __popc((C1 + kGe179) & kFlag);
+                    const int lo_idx = kLevels - n179;        // levels 0..lo_idx-1 surely have C <= 220: med >  LO
+                    const int hi_idx = kLevels - n263;        // level hi_idx surely has C >= 221:        med <= HI
+                    const int LO = lo_idx > 0 ? lv[lo_idx - 1] : -1;
+                    const int HI = hi_idx < kLevels ? lv[hi_idx] : 255;
+                    const int U1 = min(max(LO - thr + 1, 0), 255);     // defect if g <  U1
+                    const int U4 = min(HI + thr, 255);                 // defect if g >  U4
+                    const int U2 = max(HI - thr, 0);                   // clean needs g >= U2
+                    const int U3 = min(LO + thr + 1, 255);             // clean needs g <= U3
+                    cw = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
+                    // min / max of the cell's 9 pixels (clamped at the crop edge: duplicates are harmless)
+                    const int x0 = kCell * k, y0 = kCell * cj;
+                    const uint8_t* r0 = gray + min(y0, hm1) * g.gp;
+                    const uint8_t* r1 = gray + min(y0 + 1, hm1) * g.gp;
+                    const uint8_t* r2 = gray + min(y0 + 2, hm1) * g.gp;
+                    const int xa = min(x0, wm1), xb = min(x0 + 1, wm1), xc = min(x0 + 2, wm1);
+                    const int a0 = r0[xa], a1 = r0[xb], a2 = r0[xc], b0 = r1[xa], b1 = r1[xb], b2 = r1[xc],
+                              c0 = r2[xa], c1 = r2[xb], c2 = r2[xc];
+                    const int mn = min(min(min(a0, a1), min(a2, b0)), min(min(b1, b2), min(min(c0, c1), c2)));
+                    const int mx = max(max(max(a0, a1), max(a2, b0)), max(max(b1, b2), max(max(c0, c1), c2)));
+                    dirty = mn < U2 || mx > U3;
+                }
+                // append the dirty cells of this pass (one atomic per warp)
+                const unsigned dm = __ballot_sync(kFull, dirty);
+                if (dm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (dirty) {
+                        const int slot = base + __popc(dm & ((1u << lane) - 1u));
+                        if (slot < w.dirty_cap) w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)k, cw);
+                        else rank_dirty_cell(gray, g, thr, ROI, CAND, w, k, cj, cw);
                     }
                 }
             }
         }
         __syncthreads();
-        pt.acc(22);
+        pt.acc(21);
     }
-}
-
-// Exact rank counts for the pixels set in Q: CAND |= pixel iff
-// #(window <= g+thr) <= 220 or #(window <= g-thr-1) >= 221.  The pixels are
-// compacted into `list` and each is evaluated by one warp (441 window pixels over
-// 32 lanes).  Returns the number of pixels evaluated.
-__device__ inline unsigned rank_exact_list(CtaScratch& cs, const uint8_t* gray, const Geom& g, int thr, unsigned* CAND,
-                                           const unsigned* Q, unsigned* list, int cap) {
-    const int per = (g.nwords + kThreads - 1) / kThreads;
-    const int i0 = threadIdx.x * per, i1 = min(i0 + per, g.nwords);
-    unsigned n = 0, dummy = 0, total, td;
-    for (int i = i0; i < i1; ++i) n += __popc(Q[i]);
-    unsigned off = n;
-    cta_excl_scan2(cs, off, dummy, total, td);
-    if (total == 0) return 0;
-    const int lane = lane_id();
-    for (unsigned base = 0; base < total; base += (unsigned)cap) {
-        // (re)build the slice [base, base+cap) of the candidate list
-        unsigned k = off;
-        for (int i = i0; i < i1; ++i) {
-            unsigned q = Q[i];
-            int y = i / g.wpr, c = i - y * g.wpr;
-            while (q) {
-                int bpos = __ffs(q) - 1; q &= q - 1;
-                if (k >= base && k < base + (unsigned)cap) list[k - base] = ((unsigned)y << 16) | (unsigned)(c * 32 + bpos);
-                ++k;
-            }
-        }
-        __syncthreads();
-        const unsigned cnt = min((unsigned)cap, total - base);
-        for (unsigned k2 = warp_id(); k2 < cnt; k2 += kWarps) {
-            unsigned ent = list[k2];
-            int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-            int gv = gray[y * g.gp + x];
-            int pa = gv + thr, pb = gv - thr - 1;
-            int vals[14];
-#pragma unroll
-            for (int k = 0; k < 14; ++k) {
-                int e = lane + 32 * k;
-                int dy = e / 21, dx = e - dy * 21;
-                int yy = min(max(y + dy - 10, 0), g.h - 1), xx = min(max(x + dx - 10, 0), g.w - 1);
-                vals[k] = e < 441 ? (int)gray[yy * g.gp + xx] : 256;
-            }
-            unsigned ca = 0, cb = 0;
-#pragma unroll
-            for (int k = 0; k < 14; ++k) { ca += vals[k] <= pa; cb += vals[k] <= pb; }
-            ca = __reduce_add_sync(kFull, ca);
-            cb = __reduce_add_sync(kFull, cb);
-            if (lane == 0 && (ca <= 220 || cb >= 221)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
-        }
-        __syncthreads();
+    // ---- dirty cells: per-pixel classification ----------------------------------------
+    const int nd = min(w.counters[0], w.dirty_cap);
+    for (int i = tid; i < nd; i += kThreads) {
+        const uint2 e = w.dirty[i];
+        rank_dirty_cell(gray, g, thr, ROI, CAND, w, (int)(e.x & 0xffffu), (int)(e.x >> 16), e.y);
     }
+    __syncthreads();
+    pt.acc(22);
+    // ---- ambiguous pixels: exact rank counts, one warp per pixel -------------------------
+    const int ne = min(w.counters[1], w.exact_cap);
+    for (int k2 = warp; k2 < ne; k2 += kWarps) {
+        const unsigned ent = w.exact[k2];
+        const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+        const int gv = gray[y * g.gp + x];
+        const int pa = gv + thr, pb = gv - thr - 1;
+        int vals[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {
+            const int e = lane + 32 * k;
+            const int dy = e / 21, dx = e - dy * 21;
+            const int yy = min(max(y + dy - 10, 0), hm1), xx = min(max(x + dx - 10, 0), wm1);
+            vals[k] = e < 441 ? (int)gray[yy * g.gp + xx] : 256;
+        }
+        unsigned ca = 0, cb = 0;
+#pragma unroll
+        for (int k = 0; k < 14; ++k) { ca += vals[k] <= pa; cb += vals[k] <= pb; }
+        ca = __reduce_add_sync(kFull, ca);
+        cb = __reduce_add_sync(kFull, cb);
+        if (lane == 0 && (ca <= 220 || cb >= 221)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+    }
+    __syncthreads();
+    const int total = w.counters[2];
+    __syncthreads();
+    (void)cs_;
     return total;
 }
 

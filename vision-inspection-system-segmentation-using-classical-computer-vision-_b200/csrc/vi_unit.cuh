@@ -321,27 +321,33 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     // ---- P11: median residual -------------------------------------------------
     const int thr = a.p.threshold;
     select_levels(sh, npix, thr);
-    if (rank_cs_pitch(g.w) <= 32 * kSegL && rank_ws_bytes(g.w) <= plan.ws_bytes) {
-        RankWs rw = rank_ws_carve(WS, g.w);
+    for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
+    int n_amb;
+    if (g.w <= kThreads && rank_ws_bytes(g.w) <= plan.ws_bytes) {
+        RankWs rw = rank_ws_carve(WS, g.w, MA, MB, plan.mask_bytes);
         rank_tables(sh.levels, rw);
         __syncthreads();
         pt.tick();   // 10 levels + tables
-        rank_stage_lattice(gray, g, rw, sh.levels, thr, MA, MB, pt);
-        pt.tick();   // 11 rank counts
+        n_amb = rank_stage_lattice(sh.cs, gray, g, rw, sh.levels, thr, MD, MC, pt);
+        pt.tick();   // 11 rank stage remainder
     } else {
-        for (int i = tid; i < g.nwords; i += kThreads) { MA[i] = 0; MB[i] = row_mask_of(g, i % g.wpr); }
+        // units wider than the column-per-thread pass: exact rank count for every ROI pixel
         __syncthreads();
+        for (int i = tid; i < g.nwords; i += kThreads) {
+            unsigned q = MD[i], add = 0;
+            const int y = i / g.wpr, c = i - y * g.wpr;
+            while (q) {
+                const int bpos = __ffs(q) - 1; q &= q - 1;
+                if (rank_exact_pixel_thread(gray, g, thr, c * 32 + bpos, y)) add |= 1u << bpos;
+            }
+            MC[i] = add;
+        }
+        __syncthreads();
+        n_amb = (int)roi_area;
         pt.tick();
         pt.tick();
     }
-    for (int i = tid; i < g.nwords; i += kThreads) {
-        unsigned roi = MD[i];
-        MC[i] = MA[i] & roi;
-        MB[i] = MB[i] & ~MA[i] & roi;
-    }
-    __syncthreads();
-    unsigned n_amb = rank_exact_list(sh.cs, gray, g, thr, MC, MB, reinterpret_cast<unsigned*>(WS), plan.ws_bytes / 4);
-    pt.tick();   // 12 combine + exact rank counts
+    pt.tick();   // 12 (unused)
     // ---- P12: open with the 3x3 cross -----------------------------------------
     cross3_pass<true>(MC, MA, g); __syncthreads();
     cross3_pass<false>(MA, MB, g); __syncthreads();
@@ -387,7 +393,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     if (def_out) store_mask_bytes(ME, g, def_out);
     const int status = (n_kept > 0 && (long long)defect_area >= min_area) ? VI_STATUS_NG : VI_STATUS_OK;
     write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, n_kept > 0 ? defect_area : 0u, n_kept, status, dx, dy,
-                 cx, cy, (int)n_amb, n_runs_max);
+                 cx, cy, n_amb, n_runs_max);
     pt.tick();   // 16 defect mask out + record
 }
 
