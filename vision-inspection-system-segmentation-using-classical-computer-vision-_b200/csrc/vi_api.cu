@@ -320,7 +320,8 @@ static int fill_params(KArgs& a, const vi_params* p) {
 static int ensure_scratch(vi_ctx* c, int wmax, int hmax, int nblocks) {
     long long px = (long long)wmax * hmax;
     long long capg = (long long)hmax * (wmax / 2 + 1);
-    long long stride = ((px * 2 + 15) & ~15ll) + ((px + 15) & ~15ll) + (long long)ccl_ws_bytes((int)capg, hmax) + 256;
+    long long px4 = (long long)((wmax + 3) & ~3) * hmax;
+    long long stride = ((px * 2 + 15) & ~15ll) + ((px4 + 15) & ~15ll) + (long long)ccl_ws_bytes((int)capg, hmax) + 256;
     stride = (stride + 255) & ~255ll;
     c->scratch_stride = stride;
     return c->scratch.ensure((size_t)stride * nblocks);

@@ -97,7 +97,7 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
     const int i1 = min(i0 + per, g.nwords);
     unsigned ns = 0, ne = 0;
     for (int i = i0; i < i1; ++i) {
-        int y = i / g.wpr, c = i - y * g.wpr;
+        int y, c; word_rc(g, i, y, c);
         unsigned s, e;
         run_edges(M, g, y, c, s, e);
         ns += __popc(s);
@@ -108,7 +108,7 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
     if (pt) pt->acc(23);
     ws = ((int)R <= ws_s.cap) ? ws_s : ws_g;
     for (int i = i0; i < i1; ++i) {
-        int y = i / g.wpr, c = i - y * g.wpr;
+        int y, c; word_rc(g, i, y, c);
         unsigned s, e;
         run_edges(M, g, y, c, s, e);
         if (c == 0) ws.row_first[y] = (int)os + 1;
@@ -199,7 +199,7 @@ __device__ __forceinline__ void agg_min(unsigned* acc, bool valid, int root, uns
 template <class Pred>
 __device__ inline void ccl_paint(unsigned* dst, const unsigned* base, const Geom& g, const CclWs& ws, Pred pred) {
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-        int y = i / g.wpr, c = i - y * g.wpr;
+        int y, c; word_rc(g, i, y, c);
         int x0 = c * 32, x1 = x0 + 31;
         int j0 = ws.row_first[y], j1 = ws.row_first[y + 1];
         int lo = j0, hi = j1;                 // first run with xe >= x0

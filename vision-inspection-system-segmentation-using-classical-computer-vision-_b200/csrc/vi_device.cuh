@@ -42,7 +42,12 @@ struct Geom {
     int gp;             // gray pitch in bytes (multiple of 4, odd word count)
     int nwords;         // h * wpr
     unsigned lastmask;  // valid bits of the last word of a row
+    unsigned mwpr;      // floor(2^32 / wpr) + 1: i / wpr == __umulhi(i, mwpr) for i < 2^32 / wpr
 };
+
+// n / d for n < 2^32 / d through a precomputed m = floor(2^32 / d) + 1 (d > 1).
+__host__ __device__ inline unsigned magic_of(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
+__device__ __forceinline__ unsigned magic_div(unsigned n, unsigned d, unsigned m) { return d > 1 ? __umulhi(n, m) : n; }
 
 __host__ __device__ inline int gray_pitch(int w) {
     int words = (w + 3) / 4;
@@ -58,6 +63,7 @@ __host__ __device__ inline Geom make_geom(int w, int h) {
     g.nwords = h * g.wpr;
     int rem = w & 31;
     g.lastmask = rem ? ((1u << rem) - 1u) : 0xffffffffu;
+    g.mwpr = magic_of((unsigned)g.wpr);
     return g;
 }
 
@@ -252,6 +258,12 @@ __device__ inline unsigned long long cta_max_u64(CtaScratch& cs, unsigned long l
 // Bit-packed mask rows.  Bit x&31 of word x>>5 is pixel x; bits >= w of the last
 // word of a row are always 0.
 // ---------------------------------------------------------------------------
+// (row, word) of mask word index i
+__device__ __forceinline__ void word_rc(const Geom& g, int i, int& y, int& c) {
+    y = (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr);
+    c = i - y * g.wpr;
+}
+
 __device__ __forceinline__ unsigned row_mask_of(const Geom& g, int c) { return c == g.wpr - 1 ? g.lastmask : 0xffffffffu; }
 
 // Word c of row y; rows outside [0,h) and words outside [0,wpr) read as `fill`
@@ -287,15 +299,18 @@ __device__ __forceinline__ unsigned bit_range(int a, int b) {
 template <bool ERODE>
 __device__ inline void cross3_pass(const unsigned* src, unsigned* dst, const Geom& g) {
     const unsigned fill = ERODE ? 0xffffffffu : 0u;
+    const unsigned pad = fill & ~g.lastmask;             // padding bits of a row's last word read as `fill`
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-        int y = i / g.wpr, c = i - y * g.wpr;
-        unsigned m = mword(src, g, y, c, fill);
-        unsigned l = mword_shift(src, g, y, c, -1, fill);
-        unsigned r = mword_shift(src, g, y, c, +1, fill);
-        unsigned u = mword(src, g, y - 1, c, fill);
-        unsigned d = mword(src, g, y + 1, c, fill);
-        unsigned o = ERODE ? (m & l & r & u & d) : (m | l | r | u | d);
-        dst[i] = o & row_mask_of(g, c);
+        int y, c; word_rc(g, i, y, c);
+        const bool last = c == g.wpr - 1;
+        const unsigned m = src[i] | (last ? pad : 0u);
+        const unsigned lw = c > 0 ? src[i - 1] : fill;
+        const unsigned rw = last ? fill : (src[i + 1] | (c + 1 == g.wpr - 1 ? pad : 0u));
+        const unsigned u = y > 0 ? src[i - g.wpr] : fill;
+        const unsigned dn = y < g.h - 1 ? src[i + g.wpr] : fill;
+        const unsigned l = (m << 1) | (lw >> 31), r = (m >> 1) | (rw << 31);
+        const unsigned o = ERODE ? (m & l & r & u & dn) : (m | l | r | u | dn);
+        dst[i] = o & (last ? g.lastmask : 0xffffffffu);
     }
 }
 
@@ -308,7 +323,7 @@ __device__ inline void se_pass(const unsigned* src, unsigned* dst, const Geom& g
     const unsigned fill = ERODE ? 0xffffffffu : 0u;
     const int a = k / 2;
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-        int y = i / g.wpr, c = i - y * g.wpr;
+        int y, c; word_rc(g, i, y, c);
         unsigned o = fill;
         for (int j = 0; j < k; ++j) {
             int ys = y + j - a;
@@ -345,7 +360,7 @@ __device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* buf
     if (r <= kErodeDirectMax) {
         // horizontal: AND of the 2r+1 shifts, built from the three neighbouring words (edge pixel replicated)
         for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-            const int y = i / g.wpr, c = i - y * g.wpr;
+            int y, c; word_rc(g, i, y, c);
             const unsigned* row = cur + y * g.wpr;
             const unsigned fl = (row[0] & 1u) ? 0xffffffffu : 0u;
             const unsigned fr = ((row[g.wpr - 1] >> ((g.w - 1) & 31)) & 1u) ? 0xffffffffu : 0u;
@@ -362,7 +377,7 @@ __device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* buf
         nxt = (cur == bufA) ? bufB : bufA;
         // vertical: AND of the 2r+1 rows (edge row replicated)
         for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-            const int y = i / g.wpr, c = i - y * g.wpr;
+            int y, c; word_rc(g, i, y, c);
             unsigned v = cur[i];
             for (int d = 1; d <= r; ++d) v &= cur[max(y - d, 0) * g.wpr + c] & cur[min(y + d, g.h - 1) * g.wpr + c];
             nxt[i] = v;
@@ -374,7 +389,7 @@ __device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* buf
     while (a < r) {                                    // horizontal
         int b = (a == 0) ? 1 : ((2 * a <= r) ? a : (r - a));
         for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-            int y = i / g.wpr, c = i - y * g.wpr;
+            int y, c; word_rc(g, i, y, c);
             unsigned v = mword_shift_rep(cur, g, y, c, -b) & mword_shift_rep(cur, g, y, c, +b);
             if (a == 0) v &= cur[i];
             nxt[i] = v & row_mask_of(g, c);
@@ -388,7 +403,7 @@ __device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* buf
     while (a < r) {                                    // vertical
         int b = (a == 0) ? 1 : ((2 * a <= r) ? a : (r - a));
         for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-            int y = i / g.wpr, c = i - y * g.wpr;
+            int y, c; word_rc(g, i, y, c);
             unsigned v = cur[max(y - b, 0) * g.wpr + c] & cur[min(y + b, g.h - 1) * g.wpr + c];
             if (a == 0) v &= cur[i];
             nxt[i] = v;

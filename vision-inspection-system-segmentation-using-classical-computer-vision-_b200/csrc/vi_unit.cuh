@@ -27,7 +27,7 @@ __device__ inline int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
 // int32 labels, unit-packed [h][w]: 0 background, else acc1[root].
 __device__ inline void store_labels(const Geom& g, const CclWs& ws, int32_t* __restrict__ dst) {
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-        int y = i / g.wpr, c = i - y * g.wpr;
+        int y, c; word_rc(g, i, y, c);
         int x0 = c * 32, x1 = min(x0 + 31, g.w - 1);
         int j = ws.row_first[y], j1 = ws.row_first[y + 1];
         while (j < j1 && (int)ws.xe[j] < x0) ++j;
@@ -124,9 +124,10 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     // per-CTA global scratch: [u16 hsum][u8 blurred][run-table overflow]
     unsigned char* gs = a.scratch + (long long)blockIdx.x * a.scratch_stride;
     const long long maxpx = (long long)a.wmax * a.hmax;
+    const long long maxpx4 = (long long)((a.wmax + 3) & ~3) * a.hmax;      // blurred scratch rows are whole words
     unsigned short* g_hp = reinterpret_cast<unsigned short*>(gs);
     uint8_t* g_blur = gs + ((maxpx * 2 + 15) & ~15ll);
-    unsigned char* g_ccl = g_blur + ((maxpx + 15) & ~15ll);
+    unsigned char* g_ccl = g_blur + ((maxpx4 + 15) & ~15ll);
     const int capg = a.hmax * (a.wmax / 2 + 1);
     const CclWs ws_s = ccl_ws_carve(WS, plan.run_cap, a.hmax);
     const CclWs ws_g = ccl_ws_carve(g_ccl, capg, a.hmax);
@@ -161,7 +162,8 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         __syncthreads();
         if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
             // default path: one histogram round on min(16, n_hist) warps
-            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0);
+            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0,
+                             need_seg ? reinterpret_cast<unsigned*>(g_blur) : nullptr);
             __syncthreads();
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
             __syncthreads();
@@ -191,6 +193,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         if (need_seg) {
             // ---- P3: inverse threshold ------------------------------------------
             if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
+            else if (src_mode == 1 && plan.n_hist >= kWarps / 2) threshold_blurred(reinterpret_cast<const unsigned*>(g_blur), g, MA, otsu_t);
             else if (src_mode == 1) blur3_pass<false>(gray, g, nullptr, nullptr, kWarps, MA, otsu_t);
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             __syncthreads();
@@ -209,7 +212,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
             }
             pt.tick();   // 4 close/open
             // ---- P5: hole fill ----------------------------------------------------
-            for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i % g.wpr);
+            for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
             __syncthreads();
             int R = ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
             n_runs_max = max(n_runs_max, R);
@@ -254,7 +257,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         __syncthreads();
     }
     if (mode == MODE_FILL) {
-        for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i % g.wpr);
+        for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
         __syncthreads();
         ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
         ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
@@ -265,7 +268,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     if (mode == MODE_STATS) {
         unsigned long long n = 0, sx = 0, sy = 0;
         for (int i = tid; i < g.nwords; i += kThreads) {
-            int y = i / g.wpr, c = i - y * g.wpr;
+            int y, c; word_rc(g, i, y, c);
             unsigned m = MA[i];
             unsigned pc = __popc(m);
             unsigned pos = __popc(m & 0xAAAAAAAAu) + 2 * __popc(m & 0xCCCCCCCCu) + 4 * __popc(m & 0xF0F0F0F0u) +
@@ -335,7 +338,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         __syncthreads();
         for (int i = tid; i < g.nwords; i += kThreads) {
             unsigned q = MD[i], add = 0;
-            const int y = i / g.wpr, c = i - y * g.wpr;
+            int y, c; word_rc(g, i, y, c);
             while (q) {
                 const int bpos = __ffs(q) - 1; q &= q - 1;
                 if (rank_exact_pixel_thread(gray, g, thr, c * 32 + bpos, y)) add |= 1u << bpos;
@@ -353,7 +356,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     cross3_pass<false>(MA, MB, g); __syncthreads();
     pt.tick();   // 13 open
     // ---- P13: hole fill + per-component contour area filter ---------------------
-    for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i % g.wpr);
+    for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
     __syncthreads();
     R = ccl_build(sh.cs, MC, g, false, true, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
