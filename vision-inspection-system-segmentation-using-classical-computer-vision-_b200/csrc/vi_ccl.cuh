@@ -71,9 +71,12 @@ __device__ inline void ccl_jump(int* parent, int R) {
     while (true) {
         int changed = 0;
         for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {
-            int p = parent[i];
-            int pp = parent[p];
-            if (pp != p) { parent[i] = pp; changed = 1; }
+            const int p = parent[i];
+            int q = parent[p];
+            q = parent[q];
+            q = parent[q];
+            q = parent[q];
+            if (q != p) { parent[i] = q; changed = 1; }
         }
         if (!__syncthreads_or(changed)) break;
     }

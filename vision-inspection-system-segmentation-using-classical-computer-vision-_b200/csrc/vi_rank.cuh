@@ -35,6 +35,7 @@ namespace vi {
 constexpr int kCell = 3;
 constexpr int kLatBand = 16;             // lattice rows per band (= warps per CTA)
 constexpr int kCellsPerPass = 26;        // 32 triples per pass, 6 of them look-ahead
+constexpr int kPassBatch = 5;            // passes interleaved per lattice row (5 x 26 cells = 390 px)
 constexpr unsigned kFld = 0x00300C03u;   // 2-bit block-sum fields at the 10-bit field positions
 constexpr unsigned kFlag = 0x20080200u;  // bit 9 of each 10-bit field
 constexpr unsigned kGe263 = 249u | (249u << 10) | (249u << 20);   // field + 249 >= 512  <=>  field >= 263
@@ -170,33 +171,60 @@ __device__ inline int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, c
         for (int jj = warp; jj < j1 - j0; jj += kWarps) {
             const uint2* row = w.cs + jj * w.pitch;
             const int cj = j0 + jj;
-            for (int k0 = 0; k0 < nlx; k0 += kCellsPerPass) {
-                // triple k covers extended columns 3k+1..3k+3  <->  columns clamp(3k-9 .. 3k-7)
-                const int k = k0 + lane;
-                unsigned t0 = 0, t1 = 0;
-                if (k < ntrip) {
-                    const int c0 = kCell * k - 9;
-                    const uint2 a = row[min(max(c0, 0), wm1)], bb = row[min(max(c0 + 1, 0), wm1)],
-                                c = row[min(max(c0 + 2, 0), wm1)];
-                    t0 = a.x + bb.x + c.x; t1 = a.y + bb.y + c.y;
+            // kPassBatch passes are independent: their loads and scans are interleaved for ILP
+            for (int kb = 0; kb < nlx; kb += kCellsPerPass * kPassBatch) {
+                unsigned p0[kPassBatch], p1[kPassBatch];
+#pragma unroll
+                for (int u = 0; u < kPassBatch; ++u) {
+                    // triple k covers extended columns 3k+1..3k+3  <->  columns clamp(3k-9 .. 3k-7)
+                    const int k = kb + u * kCellsPerPass + lane;
+                    p0[u] = 0; p1[u] = 0;
+                    if (k < ntrip && kb + u * kCellsPerPass < nlx) {
+                        const int c0 = kCell * k - 9;
+                        const uint2 a = row[min(max(c0, 0), wm1)], bb = row[min(max(c0 + 1, 0), wm1)],
+                                    c = row[min(max(c0 + 2, 0), wm1)];
+                        p0[u] = a.x + bb.x + c.x; p1[u] = a.y + bb.y + c.y;
+                    }
                 }
-                unsigned p0 = t0, p1 = t1;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned x0 = __shfl_up_sync(kFull, p0, o), x1 = __shfl_up_sync(kFull, p1, o);
-                    if (lane >= o) { p0 += x0; p1 += x1; }
+#pragma unroll
+                    for (int u = 0; u < kPassBatch; ++u) {
+                        const unsigned x0 = __shfl_up_sync(kFull, p0[u], o), x1 = __shfl_up_sync(kFull, p1[u], o);
+                        if (lane >= o) { p0[u] += x0; p1[u] += x1; }
+                    }
                 }
-                // window of cell i = k: triples i..i+6 = P[lane+6] - P[lane-1]
-                const unsigned h0 = __shfl_down_sync(kFull, p0, 6), h1 = __shfl_down_sync(kFull, p1, 6);
-                unsigned l0 = __shfl_up_sync(kFull, p0, 1), l1 = __shfl_up_sync(kFull, p1, 1);
-                if (lane == 0) { l0 = 0; l1 = 0; }
-                const bool cact = lane < kCellsPerPass && k < nlx;
-                bool dirty = false;
-                unsigned cw = 0;
-                if (cact) {
-                    const unsigned C0 = h0 - l0, C1 = h1 - l1;
-                    const int n263 = __popc((C0 + kGe263) & kFlag) + __popc((C1 + kGe263) & kFlag);
-                    const int n179 = __popc((C0 + kGe179) & kFlag) + __popc((C1 + kGe179) & kFlag);
+                unsigned C0[kPassBatch], C1[kPassBatch];
+#pragma unroll
+                for (int u = 0; u < kPassBatch; ++u) {
+                    // window of cell i = k: triples i..i+6 = P[lane+6] - P[lane-1]
+                    const unsigned h0 = __shfl_down_sync(kFull, p0[u], 6), h1 = __shfl_down_sync(kFull, p1[u], 6);
+                    unsigned l0 = __shfl_up_sync(kFull, p0[u], 1), l1 = __shfl_up_sync(kFull, p1[u], 1);
+                    if (lane == 0) { l0 = 0; l1 = 0; }
+                    C0[u] = h0 - l0; C1[u] = h1 - l1;
+                }
+                bool dirty[kPassBatch];
+                unsigned cw[kPassBatch];
+                // the cell's 9 pixels (clamped at the crop edge: duplicates are harmless), all passes in flight
+                int px[kPassBatch][9];
+                const int y0 = kCell * cj;
+                const uint8_t* r0 = gray + min(y0, hm1) * g.gp;
+                const uint8_t* r1 = gray + min(y0 + 1, hm1) * g.gp;
+                const uint8_t* r2 = gray + min(y0 + 2, hm1) * g.gp;
+#pragma unroll
+                for (int u = 0; u < kPassBatch; ++u) {
+                    const int x0 = kCell * (kb + u * kCellsPerPass + lane);
+                    const int xa = min(x0, wm1), xb = min(x0 + 1, wm1), xc = min(x0 + 2, wm1);
+                    px[u][0] = r0[xa]; px[u][1] = r0[xb]; px[u][2] = r0[xc];
+                    px[u][3] = r1[xa]; px[u][4] = r1[xb]; px[u][5] = r1[xc];
+                    px[u][6] = r2[xa]; px[u][7] = r2[xb]; px[u][8] = r2[xc];
+                }
+#pragma unroll
+                for (int u = 0; u < kPassBatch; ++u) {
+                    const int k = kb + u * kCellsPerPass + lane;
+                    const bool cact = lane < kCellsPerPass && k < nlx;
+                    const int n263 = __popc((C0[u] + kGe263) & kFlag) + __popc((C1[u] + kGe263) & kFlag);
+                    const int n179 = __popc((C0[u] + kGe179) & kFlag) + __popc((C1[u] + kGe179) & kFlag);
                     const int lo_idx = kLevels - n179;        // levels 0..lo_idx-1 surely have C <= 220: med >  LO
                     const int hi_idx = kLevels - n263;        // level hi_idx surely has C >= 221:        med <= HI
                     const int LO = lo_idx > 0 ? lv[lo_idx - 1] : -1;
@@ -205,29 +233,26 @@ __device__ inline int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, c
                     const int U4 = min(HI + thr, 255);                 // defect if g >  U4
                     const int U2 = max(HI - thr, 0);                   // clean needs g >= U2
                     const int U3 = min(LO + thr + 1, 255);             // clean needs g <= U3
-                    cw = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
-                    // min / max of the cell's 9 pixels (clamped at the crop edge: duplicates are harmless)
-                    const int x0 = kCell * k, y0 = kCell * cj;
-                    const uint8_t* r0 = gray + min(y0, hm1) * g.gp;
-                    const uint8_t* r1 = gray + min(y0 + 1, hm1) * g.gp;
-                    const uint8_t* r2 = gray + min(y0 + 2, hm1) * g.gp;
-                    const int xa = min(x0, wm1), xb = min(x0 + 1, wm1), xc = min(x0 + 2, wm1);
-                    const int a0 = r0[xa], a1 = r0[xb], a2 = r0[xc], b0 = r1[xa], b1 = r1[xb], b2 = r1[xc],
-                              c0 = r2[xa], c1 = r2[xb], c2 = r2[xc];
-                    const int mn = min(min(min(a0, a1), min(a2, b0)), min(min(b1, b2), min(min(c0, c1), c2)));
-                    const int mx = max(max(max(a0, a1), max(a2, b0)), max(max(b1, b2), max(max(c0, c1), c2)));
-                    dirty = mn < U2 || mx > U3;
+                    cw[u] = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
+                    int mn = px[u][0], mx = px[u][0];
+#pragma unroll
+                    for (int t = 1; t < 9; ++t) { mn = min(mn, px[u][t]); mx = max(mx, px[u][t]); }
+                    dirty[u] = cact && (mn < U2 || mx > U3);
                 }
-                // append the dirty cells of this pass (one atomic per warp)
-                const unsigned dm = __ballot_sync(kFull, dirty);
-                if (dm) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
-                    base = __shfl_sync(kFull, base, 0);
-                    if (dirty) {
-                        const int slot = base + __popc(dm & ((1u << lane) - 1u));
-                        if (slot < w.dirty_cap) w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)k, cw);
-                        else rank_dirty_cell(gray, g, thr, ROI, CAND, w, k, cj, cw);
+#pragma unroll
+                for (int u = 0; u < kPassBatch; ++u) {
+                    // append the dirty cells of this pass (one atomic per warp)
+                    const unsigned dm = __ballot_sync(kFull, dirty[u]);
+                    if (dm) {
+                        const int k = kb + u * kCellsPerPass + lane;
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
+                        base = __shfl_sync(kFull, base, 0);
+                        if (dirty[u]) {
+                            const int slot = base + __popc(dm & ((1u << lane) - 1u));
+                            if (slot < w.dirty_cap) w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)k, cw[u]);
+                            else rank_dirty_cell(gray, g, thr, ROI, CAND, w, k, cj, cw[u]);
+                        }
                     }
                 }
             }

@@ -41,7 +41,25 @@ __device__ inline void store_labels(const Geom& g, const CclWs& ws, int32_t* __r
 }
 
 __device__ inline void zero_bytes(uint8_t* __restrict__ dst, int n) {
-    for (int e = threadIdx.x; e < n; e += kThreads) dst[e] = 0;
+    const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    for (int e = threadIdx.x; e < head; e += kThreads) dst[e] = 0;
+    const int n16 = (n - head) >> 4;
+    uint4* d16 = reinterpret_cast<uint4*>(dst + head);
+    for (int e = threadIdx.x; e < n16; e += kThreads) d16[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = head + (n16 << 4) + threadIdx.x; e < n; e += kThreads) dst[e] = 0;
+}
+
+// L2 prefetch of a unit's crop rows (issued for the CTA's next unit while this one computes).
+__device__ inline void prefetch_crop_l2(const KArgs& a, int uid) {
+    const int img = uid / a.n_units, unit = uid - img * a.n_units;
+    const int4 rc = a.rects[unit];
+    const uint8_t* base = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
+    const int lines = (rc.z + 127 + 127) >> 7;                       // 128-byte lines a row can touch
+    for (int i = threadIdx.x; i < rc.w * lines; i += kThreads) {
+        const int y = i / lines, l = i - y * lines;
+        const uint8_t* p = base + (long long)y * a.row_pitch + l * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
 }
 
 __device__ inline void select_levels(UnitShared& sh, int npix, int thr) {
@@ -151,6 +169,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     if (need_gray) {
         const uint8_t* src = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
         load_gray(src, a.row_pitch, g, gray);
+        if (uid + (int)gridDim.x < a.n_images * a.n_units) prefetch_crop_l2(a, uid + (int)gridDim.x);
         __syncthreads();
         pt.tick();   // 0 gather
         // ---- P1: blur + histogram ------------------------------------------------
@@ -162,8 +181,8 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         __syncthreads();
         if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
             // default path: one histogram round on min(16, n_hist) warps
-            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0,
-                             need_seg ? reinterpret_cast<unsigned*>(g_blur) : nullptr);
+            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr,
+                             sh.t_prev, need_seg ? reinterpret_cast<unsigned*>(g_blur) : nullptr);
             __syncthreads();
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
             __syncthreads();
@@ -193,10 +212,14 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         if (need_seg) {
             // ---- P3: inverse threshold ------------------------------------------
             if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
-            else if (src_mode == 1 && plan.n_hist >= kWarps / 2) threshold_blurred(reinterpret_cast<const unsigned*>(g_blur), g, MA, otsu_t);
-            else if (src_mode == 1) blur3_pass<false>(gray, g, nullptr, nullptr, kWarps, MA, otsu_t);
+            else if (src_mode == 1) {
+                const bool done = plan.n_hist >= kWarps / 2 &&
+                                  threshold_from_provisional(reinterpret_cast<const unsigned*>(g_blur), g, MA, sh.hist, sh.t_prev, otsu_t);
+                if (!done) blur3_pass<false>(gray, g, nullptr, nullptr, kWarps, MA, otsu_t);
+            }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             __syncthreads();
+            if (tid == 0) sh.t_prev = otsu_t;
             pt.tick();   // 3 threshold
             // ---- P4: close, open --------------------------------------------------
             if (a.se_k == 3) {
@@ -353,8 +376,17 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     pt.tick();   // 12 (unused)
     // ---- P12: open with the 3x3 cross -----------------------------------------
     cross3_pass<true>(MC, MA, g); __syncthreads();
-    cross3_pass<false>(MA, MB, g); __syncthreads();
+    cross3_pass<false>(MA, MB, g);
+    int any_resid = 0;
+    for (int i = tid; i < g.nwords; i += kThreads) any_resid |= (MA[i] != 0);       // erosion result non-empty <=> opening non-empty
+    any_resid = __syncthreads_or(any_resid);
     pt.tick();   // 13 open
+    if (!any_resid) {
+        // nothing survives the opening: the detector returns None (indexing_ui.py:1559-1560)
+        if (def_out) zero_bytes(def_out, npix);
+        write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, 0, 0, VI_STATUS_OK, dx, dy, cx, cy, n_amb, n_runs_max);
+        return;
+    }
     // ---- P13: hole fill + per-component contour area filter ---------------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
     __syncthreads();
@@ -404,6 +436,8 @@ __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ UnitShared sh;
     const int n_total = a.n_images * a.n_units;
+    if (threadIdx.x == 0) sh.t_prev = 127;
+    __syncthreads();
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
         process_unit(a, uid, smem, sh);
         __syncthreads();
