@@ -168,7 +168,10 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
 
     if (need_gray) {
         const uint8_t* src = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
-        load_gray(src, a.row_pitch, g, gray);
+        if ((a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0)
+            load_gray16(src, a.row_pitch, g, gray);
+        else
+            load_gray(src, a.row_pitch, g, gray);
         if (uid + (int)gridDim.x < a.n_images * a.n_units) prefetch_crop_l2(a, uid + (int)gridDim.x);
         __syncthreads();
         pt.tick();   // 0 gather
@@ -182,7 +185,8 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
             // default path: one histogram round on min(16, n_hist) warps
             blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr,
-                             sh.t_prev, need_seg ? reinterpret_cast<unsigned*>(g_blur) : nullptr);
+                             sh.t_prev, need_seg ? reinterpret_cast<unsigned*>(g_blur) : nullptr,
+                             need_seg ? reinterpret_cast<unsigned*>(g_blur) + g.nwords : nullptr);
             __syncthreads();
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
             __syncthreads();
@@ -214,7 +218,8 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
             if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             else if (src_mode == 1) {
                 const bool done = plan.n_hist >= kWarps / 2 &&
-                                  threshold_from_provisional(reinterpret_cast<const unsigned*>(g_blur), g, MA, sh.hist, sh.t_prev, otsu_t);
+                                  threshold_from_provisional(reinterpret_cast<const unsigned*>(g_blur), reinterpret_cast<const unsigned*>(g_blur) + g.nwords,
+                                                             gray, g, MA, sh.hist, sh.t_prev, otsu_t);
                 if (!done) blur3_pass<false>(gray, g, nullptr, nullptr, kWarps, MA, otsu_t);
             }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
