@@ -333,6 +333,53 @@ def residual_mask_rank(gray, thr: int, levels, stats: Optional[dict] = None):
     return out
 
 
+def residual_mask_lattice(gray, thr: int, levels, roi=None, stats: Optional[dict] = None):
+    """numpy twin of the CUDA rank-count stage (csrc/vi_rank.cuh): exact window
+    counts only at the centre of every 3x3 cell; |C(p) - C(q)| <= 21 * L1(p, q)
+    <= 42 inside a cell, so C(centre) >= 263 proves C >= 221 and C(centre) <= 178
+    proves C <= 220 for all nine pixels.  That brackets the median of the whole
+    cell between two levels; four thresholds per cell then decide a pixel
+    (defect / clean / ambiguous) and ambiguous pixels get an exact rank count.
+    Equals residual_mask_direct for ANY level set (tests/test_restate_vs_cv2.py)."""
+    levels = sorted(int(v) for v in levels)
+    K = len(levels)
+    h, w = gray.shape
+    g = gray.astype(np.int32)
+    ny, nx = (h + 2) // 3, (w + 2) // 3
+    # exact counts at virtual centres (3j+1, 3i+1): replicate padding also beyond the crop
+    pad = np.pad(gray, ((10, 10 + 3), (10, 10 + 3)), mode='edge')
+    cy = 3 * np.arange(ny) + 1
+    cx = 3 * np.arange(nx) + 1
+    lo_idx = np.zeros((ny, nx), np.int32)
+    n263 = np.zeros((ny, nx), np.int32)
+    for v in levels:
+        ind = (pad <= v).astype(np.int32)
+        s = np.pad(np.cumsum(np.cumsum(ind, axis=0), axis=1), ((1, 0), (1, 0)))
+        C = s[cy[:, None] + 21, cx[None, :] + 21] - s[cy[:, None], cx[None, :] + 21] \
+            - s[cy[:, None] + 21, cx[None, :]] + s[cy[:, None], cx[None, :]]
+        lo_idx += (C <= 178)
+        n263 += (C >= 263)
+    hi_idx = K - n263
+    LO = np.array([-1] + levels, np.int32)[lo_idx]
+    HI = np.array(levels + [255], np.int32)[hi_idx]
+    LOp = np.repeat(np.repeat(LO, 3, axis=0), 3, axis=1)[:h, :w]
+    HIp = np.repeat(np.repeat(HI, 3, axis=0), 3, axis=1)[:h, :w]
+    sure = (g <= LOp - thr) | (g >= HIp + thr + 1)
+    clean = (g >= HIp - thr) & (g <= LOp + thr + 1)
+    amb = ~sure & ~clean
+    if roi is not None:
+        amb &= roi
+    out = sure.copy()
+    if stats is not None:
+        stats['ambiguous'] = int(amb.sum())
+    if amb.any():
+        p10 = np.pad(gray, 10, mode='edge')
+        for y, x in zip(*np.nonzero(amb)):
+            win = p10[y:y + 21, x:x + 21]
+            out[y, x] = int((win <= g[y, x] + thr).sum()) <= 220 or int((win <= g[y, x] - thr - 1).sum()) >= 221
+    return out
+
+
 # --------------------------------------------------------------------------- K14/K15
 def contour_free_filter(mask, min_area: int, seg_area: int):
     """findContours(EXTERNAL) + contourArea + drawContours(FILLED) + area filter

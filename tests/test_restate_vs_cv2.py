@@ -136,6 +136,20 @@ def test_median21_and_rank_formulation():
                 assert np.array_equal(S.residual_mask_rank(im, thr, levels), direct), (thr, levels)
 
 
+def test_lattice_rank_formulation():
+    """The kernels' 3x3-lattice bound (csrc/vi_rank.cuh) is exact for any level set."""
+    rng = np.random.default_rng(12)
+    imgs = [_crops(1)[0][:100, :115].copy(), rng.integers(0, 256, size=(40, 47), dtype=np.uint8),
+            rng.integers(0, 256, size=(12, 15), dtype=np.uint8), rng.integers(60, 90, size=(31, 29), dtype=np.uint8),
+            cv2.GaussianBlur(rng.integers(0, 256, size=(64, 70), dtype=np.uint8), (15, 15), 0)]
+    for im in imgs:
+        for thr in (0, 8, 24, 100):
+            direct = cv2.absdiff(im, cv2.medianBlur(im, 21)) > thr
+            for levels in ([62, 70, 78, 192, 200, 208], [0, 1, 2, 3, 4, 5], [254] * 6, [10, 60, 110, 160, 210, 250]):
+                st = {}
+                assert np.array_equal(S.residual_mask_lattice(im, thr, levels, stats=st), direct), (thr, levels)
+
+
 def test_contour_free_filter():
     rng = np.random.default_rng(2)
     masks = _adversarial_masks()
