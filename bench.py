@@ -97,7 +97,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -238,7 +238,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup // 2)):
         insp.inspect_batch_host(h_frames, params, out=(h_rec, h_seg, h_def))
     barrier()
-    e2e_steps = max(1, args.steps)
+    e2e_steps = max(1, min(args.steps, 20))
     t0e = time.perf_counter()
     for _ in range(e2e_steps):
         insp.inspect_batch_host(h_frames, params, out=(h_rec, h_seg, h_def))
@@ -293,7 +293,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": algo_bytes_per_launch, "kernel": "vi_unit_kernel"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "units/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": int(n_img * H * W),
+                    "h2d_bytes_per_step": int(insp._lib.vi_host_upload_bytes(insp._ctx, n_img, W)),
+                    "h2d_note": "only frame rows covered by units are uploaded (full frames: %d B)" % (n_img * H * W),
                     "d2h_bytes_per_step": int(2 * total_px + n_img * n_units * 64)},
             "gpu_launches": args.steps,
             "clocks": clocks,
@@ -306,8 +307,8 @@ def run_gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=64, help="frames per GPU per step (configs[1] = 64)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic frames per GPU (tiled to --images)")

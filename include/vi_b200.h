@@ -122,6 +122,10 @@ int vi_inspect_batch_host(vi_ctx* ctx, const uint8_t* h_frames, int n_images, in
                           int64_t row_pitch, int64_t image_stride, const vi_params* params,
                           uint8_t* h_seg_masks, uint8_t* h_defect_masks, vi_unit_record* h_records);
 
+/* Bytes vi_inspect_batch_host uploads for n_images frames: only the frame rows that some
+ * unit covers are copied (one strided copy per merged row interval). */
+int64_t vi_host_upload_bytes(vi_ctx* ctx, int n_images, int64_t row_pitch);
+
 /* ---- per-unit compat entry points (host pointers, synchronous) ------------ */
 
 /* segmentation.segment_cell (segmentation.py:75-100): gray [h][w] -> mask 0/255. */

@@ -34,7 +34,7 @@ assert RECORD_DTYPE.itemsize == 64
 EXPORTS = [
     "vi_last_error", "vi_version", "vi_params_default", "vi_ctx_create", "vi_ctx_destroy", "vi_set_grid",
     "vi_set_exclusions", "vi_set_ref_centroids", "vi_unit_pixels", "vi_unit_offsets", "vi_inspect_batch",
-    "vi_inspect_batch_host", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
+    "vi_inspect_batch_host", "vi_host_upload_bytes", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
     "vi_label_components", "vi_detect_defects", "vi_debug_set_profile", "vi_debug_fastdiv_check",
 ]
 
@@ -72,6 +72,8 @@ def load():
     lib.vi_unit_pixels.argtypes = [vp]
     lib.vi_unit_pixels.restype = i64
     lib.vi_unit_offsets.argtypes = [vp, vp]
+    lib.vi_host_upload_bytes.argtypes = [vp, C.c_int, i64]
+    lib.vi_host_upload_bytes.restype = i64
     lib.vi_inspect_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, P(ViParams), vp, vp, vp, vp, vp]
     lib.vi_inspect_batch_host.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, P(ViParams), vp, vp, vp]
     lib.vi_segment_cell.argtypes = [vp, vp, C.c_int, C.c_int, P(ViParams), vp, P(i32)]
@@ -84,7 +86,7 @@ def load():
     lib.vi_detect_defects.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(ViParams), vp, P(i32), vp]
     for n in EXPORTS:
         f = getattr(lib, n)
-        if n not in ("vi_last_error", "vi_params_default", "vi_ctx_destroy", "vi_unit_pixels", "vi_version"):
+        if n not in ("vi_last_error", "vi_params_default", "vi_ctx_destroy", "vi_unit_pixels", "vi_version", "vi_host_upload_bytes"):
             f.restype = C.c_int
     _lib = lib
     return lib

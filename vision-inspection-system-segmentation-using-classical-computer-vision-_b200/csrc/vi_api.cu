@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "vi_unit.cuh"
@@ -234,6 +235,21 @@ extern "C" int vi_debug_set_profile(vi_ctx* c, long long* d_cycles) {
     return VI_OK;
 }
 
+extern "C" int64_t vi_host_upload_bytes(vi_ctx* c, int n_images, int64_t row_pitch) {
+    if (!c) return 0;
+    std::vector<std::pair<int, int>> iv;
+    for (const int4& r : c->grid.rects) iv.emplace_back(r.y, r.y + r.w);
+    std::sort(iv.begin(), iv.end());
+    long long rows = 0;
+    int end = -1;
+    for (const auto& p : iv) {
+        int a0 = std::max(p.first, end);
+        if (p.second > a0) rows += p.second - a0;
+        end = std::max(end, p.second);
+    }
+    return (int64_t)rows * row_pitch * n_images;
+}
+
 extern "C" int64_t vi_unit_pixels(vi_ctx* c) { return c ? c->grid.unit_px : 0; }
 
 extern "C" int vi_unit_offsets(vi_ctx* c, int64_t* out) {
@@ -413,12 +429,28 @@ extern "C" int vi_inspect_batch_host(vi_ctx* c, const uint8_t* h_frames, int n_i
         if ((rc = c->hb_def[b].ensure((size_t)upx * chunk))) return rc;
         if ((rc = c->hb_rec[b].ensure(sizeof(vi_unit_record) * (size_t)n_units * chunk))) return rc;
     }
+    // merged [y0, y1) row intervals covered by the grid
+    std::vector<std::pair<int, int>> rows;
+    {
+        std::vector<std::pair<int, int>> iv;
+        for (const int4& r : c->grid.rects) iv.emplace_back(r.y, r.y + r.w);
+        std::sort(iv.begin(), iv.end());
+        for (const auto& p : iv) {
+            if (!rows.empty() && p.first <= rows.back().second) rows.back().second = std::max(rows.back().second, p.second);
+            else rows.push_back(p);
+        }
+    }
     int slot = 0;
     for (int i0 = 0; i0 < n_images; i0 += chunk, slot ^= 1) {
         const int n = std::min(chunk, n_images - i0);
         cudaStream_t st = c->streams[slot];
         // the slot's previous chunk (two iterations ago) is ordered before this one on the same stream
-        CU(cudaMemcpyAsync(c->hb_frames[slot].p, h_frames + (size_t)i0 * image_stride, frame_bytes * n, cudaMemcpyHostToDevice, st));
+        // upload only the frame rows some unit covers: one strided copy per merged row interval
+        for (const auto& iv : rows) {
+            const size_t off = (size_t)iv.first * row_pitch, bytes = (size_t)(iv.second - iv.first) * row_pitch;
+            CU(cudaMemcpy2DAsync((uint8_t*)c->hb_frames[slot].p + off, frame_bytes, h_frames + (size_t)i0 * image_stride + off,
+                                 (size_t)image_stride, bytes, n, cudaMemcpyHostToDevice, st));
+        }
         KArgs a;
         base_args(c, a, c->grid);
         if ((rc = fill_params(a, params))) return rc;
