@@ -184,9 +184,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         __syncthreads();
         if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
             // default path: one histogram round on min(16, n_hist) warps
-            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr,
-                             sh.t_prev, need_seg ? reinterpret_cast<unsigned*>(g_blur) : nullptr,
-                             need_seg ? reinterpret_cast<unsigned*>(g_blur) + g.nwords : nullptr);
+            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0);
             __syncthreads();
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
             __syncthreads();
@@ -217,14 +215,13 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
             // ---- P3: inverse threshold ------------------------------------------
             if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             else if (src_mode == 1) {
-                const bool done = plan.n_hist >= kWarps / 2 &&
-                                  threshold_from_provisional(reinterpret_cast<const unsigned*>(g_blur), reinterpret_cast<const unsigned*>(g_blur) + g.nwords,
-                                                             gray, g, MA, sh.hist, sh.t_prev, otsu_t);
-                if (!done) blur3_pass<false>(gray, g, nullptr, nullptr, kWarps, MA, otsu_t);
+                threshold_gray(gray, g, MB, otsu_t);
+                __syncthreads();
+                pt.acc(29);
+                threshold_band(gray, g, MB, MA, otsu_t);
             }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             __syncthreads();
-            if (tid == 0) sh.t_prev = otsu_t;
             pt.tick();   // 3 threshold
             // ---- P4: close, open --------------------------------------------------
             if (a.se_k == 3) {
@@ -441,8 +438,6 @@ __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ UnitShared sh;
     const int n_total = a.n_images * a.n_units;
-    if (threadIdx.x == 0) sh.t_prev = 127;
-    __syncthreads();
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
         process_unit(a, uid, smem, sh);
         __syncthreads();
