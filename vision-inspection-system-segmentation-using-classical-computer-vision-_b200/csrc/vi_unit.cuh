@@ -218,7 +218,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
                 threshold_gray(gray, g, MB, otsu_t);
                 __syncthreads();
                 pt.acc(29);
-                threshold_band(gray, g, MB, MA, otsu_t);
+                threshold_band(gray, g, MB, MA, MC, otsu_t);
             }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             __syncthreads();
