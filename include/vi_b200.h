@@ -30,7 +30,7 @@ extern "C" {
 #define VI_OK 0
 #define VI_ERR_ARG (-1)         /* bad argument (null pointer, rect outside frame, bad size) */
 #define VI_ERR_CUDA (-2)        /* CUDA runtime / launch failure                              */
-#define VI_ERR_UNSUPPORTED (-3) /* valid reference option not built yet (adaptive, canny)    */
+#define VI_ERR_UNSUPPORTED (-3) /* valid reference option not built yet (canny)              */
 #define VI_ERR_TOO_LARGE (-4)   /* unit does not fit the shared-memory-resident path          */
 
 /* vi_unit_record.status */
@@ -158,6 +158,10 @@ int vi_debug_set_profile(vi_ctx* ctx, long long* d_cycles);
 /* Compares the reciprocal-based division of the Otsu recurrence with the IEEE divide on
  * n_samples pseudo-random operand pairs; *mismatches must come back 0. */
 int vi_debug_fastdiv_check(vi_ctx* ctx, long long n_samples, unsigned long long seed, long long* mismatches);
+
+/* Host only: the float32 taps of the adaptive threshold's Gaussian mean for an odd block size
+ * (cv2.getGaussianKernel(bs, 0, CV_32F) as cv2.adaptiveThreshold uses it, segmentation.py:85). */
+int vi_debug_adaptive_taps(int block_size, float* out_taps);
 
 #ifdef __cplusplus
 }

@@ -405,13 +405,61 @@ def contour_free_filter(mask, min_area: int, seg_area: int):
     return (keep[lab] * 255).astype(np.uint8), int(keep.sum())
 
 
+# --------------------------------------------------------------------------- adaptive threshold
+_SMALL_GAUSS_F32 = dict(_SMALL_GAUSS)
+_SMALL_GAUSS_F32[9] = [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256]
+
+
+def gaussian_kernel_f32(k: int):
+    """cv2.getGaussianKernel(k, 0, CV_32F): the taps of adaptiveThreshold's Gaussian mean
+    (OpenCV 4.13 hard-codes the kernels up to 9 taps)."""
+    if k in _SMALL_GAUSS_F32:
+        return np.array(_SMALL_GAUSS_F32[k], np.float32)
+    sigma = ((k - 1) * 0.5 - 1) * 0.3 + 0.8
+    s2 = -0.5 / (sigma * sigma)
+    kern = np.array([math.exp(s2 * (i - (k - 1) * 0.5) ** 2) for i in range(k)], np.float64)
+    return (kern * (1.0 / kern.sum())).astype(np.float32)
+
+
+def _fma32(a, b, c):
+    # float32 fused multiply-add: the float64 product of two float32 is exact; the one extra
+    # rounding of the float64 sum can differ from a true FMA only on a double-rounding tie
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+
+def adaptive_inv_mask(img, block: int, C: int):
+    """cv2.adaptiveThreshold(img, 255, ADAPTIVE_THRESH_GAUSSIAN_C, THRESH_BINARY_INV, bs, C)
+    (segmentation.py:83-86): float32 separable Gaussian with BORDER_REPLICATE in the
+    operation order of OpenCV's vector path (rows: tap-by-tap FMAs from the first product; columns:
+    centre * k[r], then FMAs of (below + above) * k[r+i]), mean rounded half-to-even to uint8,
+    255 where img - mean <= -C."""
+    bs = max(3, int(block) | 1)
+    k = gaussian_kernel_f32(bs)
+    r = bs // 2
+    h, w = img.shape
+    p = np.pad(img, ((0, 0), (r, r)), mode='edge').astype(np.float32)
+    s = p[:, 0:w] * k[0]
+    for i in range(1, bs):
+        s = _fma32(p[:, i:i + w], k[i], s)
+    q = np.pad(s, ((r, r), (0, 0)), mode='edge')
+    o = q[r:r + h] * k[r]
+    for i in range(1, r + 1):
+        o = _fma32(q[r + i:r + i + h] + q[r - i:r - i + h], k[r + i], o)
+    mean = np.clip(np.rint(o), 0, 255).astype(np.int32)
+    return np.where(img.astype(np.int32) - mean <= -int(C), 255, 0).astype(np.uint8)
+
+
 # --------------------------------------------------------------------------- full unit
-def segment_cell(gray, method='otsu', gaussian_blur=3, morph_kernel=3, info: Optional[dict] = None):
-    """segmentation.py:75-100, Otsu branch."""
+def segment_cell(gray, method='otsu', gaussian_blur=3, morph_kernel=3, info: Optional[dict] = None,
+                 adapt_block=51, adapt_C=10):
+    """segmentation.py:75-100."""
     img = gaussian_blur_u8(gray, gaussian_blur)
-    t, mask = otsu_inv_mask(img)
-    if info is not None:
-        info['otsu_t'] = t
+    if method == 'adaptive':
+        mask = adaptive_inv_mask(img, adapt_block, adapt_C)
+    else:
+        t, mask = otsu_inv_mask(img)
+        if info is not None:
+            info['otsu_t'] = t
     mask = morph_close_open(mask, morph_kernel)
     return fill_holes_4bg(mask)
 

@@ -184,7 +184,42 @@ def _run_batch(insp, g, fi, params, is_reference, refc, exclusions, host=False, 
     return rec, seg.cpu().numpy(), dfm.cpu().numpy(), (lab.cpu().numpy() if labels else None)
 
 
-@pytest.mark.parametrize("name", ["config1", "config4", "config5", "blur5_morph5"])
+ADAPT_CFGS = [dict(), dict(adapt_block=11, adapt_C=-3), dict(adapt_block=3, adapt_C=0), dict(adapt_block=201, adapt_C=10),
+              dict(adapt_block=50, adapt_C=5, gaussian_blur=0), dict(adapt_block=21, adapt_C=-50, gaussian_blur=7, morph_kernel=5),
+              dict(adapt_block=9, adapt_C=2, morph_kernel=0), dict(adapt_block=2, adapt_C=50)]
+
+
+def test_segment_cell_adaptive(insp):
+    """segmentation.py:83-86.  The adaptive mean is a float32 Gaussian: the north star's +-1 LSB class.  The CUDA path
+    follows OpenCV's vector path operation for operation; a pixel can differ only where the float mean lands on a .5
+    tie in the columns OpenCV's scalar tail handles.  Stated bound: <= 1e-4 of the pixels of the raw threshold mask
+    (blur=0, morph=0 rows below compare it directly); measured: 0."""
+    from vi_b200 import segmentation as seg
+    rng = np.random.default_rng(31)
+    imgs = crops(3) + [rng.integers(0, 256, size=(64, 97), dtype=np.uint8), np.full((40, 50), 123, np.uint8),
+                       np.tile(np.linspace(0, 255, 120).astype(np.uint8), (90, 1)),
+                       rng.integers(0, 256, size=(12, 15), dtype=np.uint8), rng.integers(0, 256, size=(1, 1), dtype=np.uint8),
+                       cv2.GaussianBlur(rng.integers(0, 256, size=(200, 203), dtype=np.uint8), (15, 15), 0)]
+    bad = tot = 0
+    for kw in ADAPT_CFGS:
+        for im in imgs:
+            ref = R.segment_cell(im, method='adaptive', **kw)
+            got = seg.segment_cell(im, method='adaptive', **kw)
+            assert got.shape == ref.shape and got.dtype == np.uint8 and set(np.unique(got)) <= {0, 255}
+            bad += int((got != ref).sum()); tot += ref.size
+            # the raw adaptive threshold mask, no morphology or hole fill in between
+            raw_ref = cv2.adaptiveThreshold(im, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY_INV,
+                                            max(3, kw.get('adapt_block', 51) | 1), kw.get('adapt_C', 10))
+            p = vi_b200.default_params(seg_method='adaptive', gaussian_blur=0, morph_kernel=0,
+                                       adapt_block=kw.get('adapt_block', 51), adapt_C=kw.get('adapt_C', 10))
+            raw_got = insp.segment_cell(im, p)
+            raw_ref = R.fill_internal_holes(raw_ref)
+            bad += int((raw_got != raw_ref).sum()); tot += raw_ref.size
+    print(f"adaptive: {bad} mismatching pixels of {tot}")
+    assert bad <= 1e-4 * tot, (bad, tot)
+
+
+@pytest.mark.parametrize("name", ["config1", "config4", "config5", "blur5_morph5", "adaptive"])
 def test_batch_matches_reference_goldens(insp, golden, name):
     g = golden(name)
     meta = g.meta
@@ -277,7 +312,7 @@ def test_error_paths(insp):
         seg.fill_internal_holes(np.zeros((2, 2, 2), np.uint8))
     assert seg.mask_stats(np.zeros((4, 4), np.uint8)) == {'area': 0, 'centroid': (0, 0)}
     with pytest.raises(vi_b200.ViError):
-        seg.segment_cell(np.zeros((8, 8), np.uint8), method='adaptive')     # not built yet: fails loudly
+        seg.detect_defects(np.zeros((8, 8), np.uint8), np.full((8, 8), 255, np.uint8), method='canny')   # not built yet: fails loudly
     with pytest.raises(vi_b200.ViError):
         insp.set_grid([(0, 0, 2000, 2000)])                                  # does not fit shared memory
     insp.set_grid([(10, 10, 50, 50)])

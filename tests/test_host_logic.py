@@ -36,6 +36,17 @@ def test_struct_layouts_match_the_header():
     assert (p.defect_method, p.threshold, p.min_area, p.erode_px, p.median_ksize, p.max_area_frac) == (0, 24, 20, 6, 21, 0.98)
 
 
+def test_adaptive_taps_host_function_matches_cv2():
+    """Host-only export: float32 taps of the adaptive mean, bit-equal to cv2 for the widget range 3..201."""
+    cv2 = pytest.importorskip("cv2")
+    lib = _lib.load()
+    for bs in range(3, 202, 2):
+        out = np.zeros(bs, np.float32)
+        assert lib.vi_debug_adaptive_taps(bs, out.ctypes.data) == 0
+        assert np.array_equal(out, cv2.getGaussianKernel(bs, 0, cv2.CV_32F).ravel()), bs
+    assert lib.vi_debug_adaptive_taps(4, np.zeros(4, np.float32).ctypes.data) != 0
+
+
 def test_compute_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():

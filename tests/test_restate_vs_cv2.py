@@ -57,6 +57,24 @@ def test_gaussian_bit_exact(k):
         assert np.array_equal(S.gaussian_blur_u8(img, k), cv2.GaussianBlur(img, (kk, kk), 0)), k
 
 
+def test_adaptive_taps_and_mask():
+    """float32 Gaussian mean, the +-1 LSB class.  Taps are bit-equal to cv2's for every block size of the
+    widget range; the mask restatement may differ from cv2 only at .5 ties of the float mean (cv2's scalar tail columns,
+    numpy's emulated FMA): stated bound 1e-4 of the pixels, measured here 0."""
+    for bs in range(3, 202, 2):
+        assert np.array_equal(S.gaussian_kernel_f32(bs), cv2.getGaussianKernel(bs, 0, cv2.CV_32F).ravel()), bs
+    rng = np.random.default_rng(2)
+    imgs = [_crops(1)[0], rng.integers(0, 256, size=(61, 47), dtype=np.uint8),
+            cv2.GaussianBlur(rng.integers(0, 256, size=(90, 100), dtype=np.uint8), (9, 9), 0)]
+    bad = tot = 0
+    for bs, C in ((51, 10), (11, -3), (3, 0), (201, 10), (21, -50), (9, 2)):
+        for im in imgs:
+            ref = cv2.adaptiveThreshold(im, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY_INV, bs, C)
+            got = S.adaptive_inv_mask(im, bs, C)
+            bad += int((got != ref).sum()); tot += ref.size
+    assert bad <= 1e-4 * tot, (bad, tot)
+
+
 def test_otsu_matches_cv2():
     rng = np.random.default_rng(0)
     imgs = _crops(4)

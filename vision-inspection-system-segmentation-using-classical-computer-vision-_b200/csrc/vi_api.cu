@@ -70,6 +70,7 @@ struct vi_ctx {
     int is_reference = 0;
     DevBuf scratch;
     long long scratch_stride = 0;
+    long long scratch_f32_off = 0;
     // compat / host-batch staging
     DevBuf st_in, st_aux, st_out, st_out2, st_rec, st_stats, st_lab;
     DevBuf hb_frames[2], hb_seg[2], hb_def[2], hb_rec[2];
@@ -291,6 +292,31 @@ static void gaussian_taps_q8(int k, int* q) {
     q[k / 2] = 256 - 2 * acc;
 }
 
+// cv2.getGaussianKernel(bs, 0, CV_32F): the float32 taps of adaptiveThreshold's Gaussian mean
+// (hard-coded tables up to 9 taps in OpenCV 4.13, else exp(-x^2 / 2 sigma^2) normalised in double).
+static void gaussian_taps_f32(int k, float* out) {
+    static const double s3[] = {0.25, 0.5, 0.25};
+    static const double s5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625};
+    static const double s7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+    static const double s9[] = {4.0 / 256, 13.0 / 256, 30.0 / 256, 51.0 / 256, 60.0 / 256, 51.0 / 256, 30.0 / 256, 13.0 / 256, 4.0 / 256};
+    const double* small = k == 3 ? s3 : k == 5 ? s5 : k == 7 ? s7 : k == 9 ? s9 : nullptr;
+    if (k == 1) { out[0] = 1.0f; return; }
+    if (small) { for (int i = 0; i < k; ++i) out[i] = (float)small[i]; return; }
+    std::vector<double> kern(k);
+    const double sigma = ((k - 1) * 0.5 - 1) * 0.3 + 0.8;
+    const double s2 = -0.5 / (sigma * sigma);
+    double tot = 0;
+    for (int i = 0; i < k; ++i) { const double x = i - (k - 1) * 0.5; kern[i] = std::exp(s2 * x * x); tot += kern[i]; }
+    const double inv = 1.0 / tot;
+    for (int i = 0; i < k; ++i) out[i] = (float)(kern[i] * inv);
+}
+
+extern "C" int vi_debug_adaptive_taps(int block_size, float* out) {
+    if (!out || block_size < 1 || block_size > kMaxAdapt || block_size % 2 == 0) return fail(VI_ERR_ARG, "vi_debug_adaptive_taps: block size %d", block_size);
+    gaussian_taps_f32(block_size, out);
+    return VI_OK;
+}
+
 static void ellipse_spans(int k, signed char* lo, signed char* hi) {
     // cv2.getStructuringElement(MORPH_ELLIPSE,(k,k)) as per-row offset spans
     int r = k / 2, c = k / 2;
@@ -311,7 +337,14 @@ static void ellipse_spans(int k, signed char* lo, signed char* hi) {
 static int fill_params(KArgs& a, const vi_params* p) {
     if (!p) return fail(VI_ERR_ARG, "params is null");
     a.p = *p;
-    if (p->seg_method == 1) return fail(VI_ERR_UNSUPPORTED, "seg_method 'adaptive' (segmentation.py:83-86) is not built yet");
+    if (p->seg_method != 0 && p->seg_method != 1) return fail(VI_ERR_ARG, "seg_method %d (0 otsu, 1 adaptive)", p->seg_method);
+    a.adapt_bs = 0;
+    if (p->seg_method == 1) {
+        const int bs = std::max(3, p->adapt_block | 1);                                                     // segmentation.py:84
+        if (bs > kMaxAdapt) return fail(VI_ERR_ARG, "adapt_block %d: block wider than %d", p->adapt_block, kMaxAdapt);
+        a.adapt_bs = bs;
+        gaussian_taps_f32(bs, a.ataps);
+    }
     if (p->defect_method == 1) return fail(VI_ERR_UNSUPPORTED, "defect_method 'canny' (indexing_ui.py:1536-1539) is not built yet");
     if (p->median_ksize != 21) return fail(VI_ERR_UNSUPPORTED, "median_ksize must be 21 (indexing_ui.py:1522)");
     if (p->threshold < 0 || p->threshold > 255) return fail(VI_ERR_ARG, "threshold %d outside 0..255", p->threshold);
@@ -322,7 +355,7 @@ static int fill_params(KArgs& a, const vi_params* p) {
     if (k > kMaxTaps) return fail(VI_ERR_ARG, "gaussian_blur %d: kernel wider than %d", p->gaussian_blur, kMaxTaps);
     a.blur_k = k;
     memset(a.taps, 0, sizeof a.taps);
-    if (k > 3) gaussian_taps_q8(k, a.taps);
+    if (k >= 3) gaussian_taps_q8(k, a.taps);
     int mk = p->morph_kernel > 0 ? std::max(1, p->morph_kernel) : 0;                                   // segmentation.py:91-92
     if (mk == 1) mk = 0;                                   // a 1x1 element is the identity
     if (mk > kMaxSE) return fail(VI_ERR_ARG, "morph_kernel %d: element wider than %d", p->morph_kernel, kMaxSE);
@@ -333,12 +366,14 @@ static int fill_params(KArgs& a, const vi_params* p) {
     return VI_OK;
 }
 
-static int ensure_scratch(vi_ctx* c, int wmax, int hmax, int nblocks) {
+static int ensure_scratch(vi_ctx* c, int wmax, int hmax, int nblocks, bool f32_plane) {
     long long px = (long long)wmax * hmax;
     long long capg = (long long)hmax * (wmax / 2 + 1);
     long long px4 = (long long)((wmax + 3) & ~3) * hmax;
     long long stride = ((px * 2 + 15) & ~15ll) + ((px4 + 15) & ~15ll) + (long long)ccl_ws_bytes((int)capg, hmax) + 256;
     stride = (stride + 255) & ~255ll;
+    c->scratch_f32_off = stride;
+    if (f32_plane) stride += (px * 4 + 255) & ~255ll;       // float plane of the adaptive mean, only when asked for
     c->scratch_stride = stride;
     return c->scratch.ensure((size_t)stride * nblocks);
 }
@@ -351,9 +386,10 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     if (n_total > 0x7fffffffll) return fail(VI_ERR_ARG, "too many units in one call");
     int nblocks = (int)std::min<long long>(n_total, c->sm_count);
     int rc;
-    if ((rc = ensure_scratch(c, gs.wmax, gs.hmax, 2 * c->sm_count))) return rc;
+    if ((rc = ensure_scratch(c, gs.wmax, gs.hmax, 2 * c->sm_count, a.p.seg_method == 1))) return rc;
     a.scratch = (uint8_t*)c->scratch.p + (size_t)slot * c->sm_count * c->scratch_stride;
     a.scratch_stride = c->scratch_stride;
+    a.scratch_f32_off = c->scratch_f32_off;
     a.wmax = gs.wmax; a.hmax = gs.hmax;
     a.plan = gs.plan;
     a.prof = (&gs == &c->grid) ? c->prof : nullptr;

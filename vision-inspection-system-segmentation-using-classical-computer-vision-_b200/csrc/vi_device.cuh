@@ -19,6 +19,7 @@ constexpr int kHistBytes = kHistWords * 4;
 constexpr int kMaxExcl = 32;
 constexpr int kMaxTaps = 33;
 constexpr int kMaxSE = 33;
+constexpr int kMaxAdapt = 201;      // widest adaptive-threshold block (the reference's widget range, indexing_ui.py:805)
 constexpr int kLevels = 6;         // rank-count levels of the median stage (two words of three 10-bit fields)
 constexpr int kBandRows = 16;      // output rows per band of the rank-count stage
 constexpr int kSegL = 11;         // columns per lane in the horizontal prefix of the rank-count stage
@@ -130,6 +131,8 @@ struct KArgs {
     int blur_k;                     // 0 skip, 3 fast path, else general (odd)
     int taps[kMaxTaps];             // 8.8 fixed-point Gaussian taps for the general path
     int se_k;                       // 0 skip, 3 = cross fast path, else general
+    int adapt_bs;                   // adaptive threshold block size (odd, >= 3); used when p.seg_method == 1
+    float ataps[kMaxAdapt];         // float32 Gaussian taps of the adaptive mean (cv2.getGaussianKernel(bs, 0, CV_32F))
     signed char se_lo[kMaxSE], se_hi[kMaxSE];   // per SE row: x-offset span [lo,hi] relative to the anchor (lo>hi: empty)
     uint8_t* seg_out;
     uint8_t* def_out;
@@ -141,6 +144,7 @@ struct KArgs {
     int erode_r;                    // MODE_ERODE radius
     uint8_t* scratch;               // per-CTA global scratch (general blur path, run-table overflow)
     long long scratch_stride;
+    long long scratch_f32_off;      // offset of the float plane inside a CTA's scratch (adaptive threshold only)
     int wmax, hmax;
     long long* prof;                // diagnostics: [n_total][32] per-phase cycle counts, or null
     SmemPlan plan;

@@ -176,8 +176,20 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         __syncthreads();
         pt.tick();   // 0 gather
         // ---- P1: blur + histogram ------------------------------------------------
-        const int src_mode = (mode == MODE_DETECT || a.blur_k == 0) ? 0 : (a.blur_k == 3 ? 1 : 2);
-        if (src_mode == 2) blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
+        int src_mode = (mode == MODE_DETECT || a.blur_k == 0) ? 0 : (a.blur_k == 3 ? 1 : 2);
+        const bool adaptive = need_seg && a.p.seg_method == 1;
+        if (adaptive) {
+            // the adaptive mean reads the blurred crop from global scratch whatever the blur size
+            if (a.blur_k == 0) {
+                for (int e = tid; e < npix; e += kThreads) { const int y = e / g.w; g_blur[e] = gray[y * g.gp + (e - y * g.w)]; }
+                __syncthreads();
+            } else {
+                blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
+            }
+            src_mode = 2;
+        } else if (src_mode == 2) {
+            blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
+        }
         unsigned* hist_base = reinterpret_cast<unsigned*>(Rg);
         for (int i = tid; i < plan.n_hist * kHistWords; i += kThreads) hist_base[i] = 0;
         if (tid < 256) sh.hist[tid] = 0;
@@ -213,7 +225,9 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
 
         if (need_seg) {
             // ---- P3: inverse threshold ------------------------------------------
-            if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
+            if (adaptive)
+                adaptive_threshold(g_blur, g, a.adapt_bs, a.ataps, a.p.adapt_C, reinterpret_cast<float*>(gs + a.scratch_f32_off), MA);
+            else if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             else if (src_mode == 1) {
                 threshold_gray(gray, g, MB, otsu_t);
                 __syncthreads();
