@@ -30,7 +30,7 @@ extern "C" {
 #define VI_OK 0
 #define VI_ERR_ARG (-1)         /* bad argument (null pointer, rect outside frame, bad size) */
 #define VI_ERR_CUDA (-2)        /* CUDA runtime / launch failure                              */
-#define VI_ERR_UNSUPPORTED (-3) /* valid reference option not built yet (canny)              */
+#define VI_ERR_UNSUPPORTED (-3) /* a value the reference itself never uses (e.g. median_ksize != 21) */
 #define VI_ERR_TOO_LARGE (-4)   /* unit does not fit the shared-memory-resident path          */
 
 /* vi_unit_record.status */

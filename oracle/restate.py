@@ -449,6 +449,47 @@ def adaptive_inv_mask(img, block: int, C: int):
     return np.where(img.astype(np.int32) - mean <= -int(C), 255, 0).astype(np.uint8)
 
 
+# --------------------------------------------------------------------------- canny
+def canny_edges(gray, low: int, high: int):
+    """cv2.Canny(gray, low, high) with aperture 3 and the L1 gradient (indexing_ui.py:1537), integer
+    throughout: Sobel with BORDER_REPLICATE, m = |gx| + |gy| (0 outside the crop), non-maximum
+    suppression by the 15-bit fixed-point tan 22.5 / tan 67.5 sectors, candidates m > low, strong
+    m > high, hysteresis = candidates 8-connected to a strong candidate."""
+    if low > high:
+        low, high = high, low
+    low, high = int(math.floor(low)), int(math.floor(high))
+    h, w = gray.shape
+    g = np.pad(gray.astype(np.int32), 1, mode='edge')
+
+    def px(dy, dx):
+        return g[1 + dy:1 + dy + h, 1 + dx:1 + dx + w]
+    gx = (px(-1, 1) + 2 * px(0, 1) + px(1, 1)) - (px(-1, -1) + 2 * px(0, -1) + px(1, -1))
+    gy = (px(1, -1) + 2 * px(1, 0) + px(1, 1)) - (px(-1, -1) + 2 * px(-1, 0) + px(-1, 1))
+    m = np.abs(gx) + np.abs(gy)
+    mp = np.pad(m, 1, mode='constant')
+
+    def mg(dy, dx):
+        return mp[1 + dy:1 + dy + h, 1 + dx:1 + dx + w]
+    ax = np.abs(gx).astype(np.int64)
+    ay15 = np.abs(gy).astype(np.int64) << 15
+    tg22x = ax * 13573
+    tg67x = tg22x + (ax << 16)
+    horiz = ay15 < tg22x
+    vert = ~horiz & (ay15 > tg67x)
+    diag = ~horiz & ~vert
+    same_sign = ~((gx ^ gy) < 0)
+    ok_h = (m > mg(0, -1)) & (m >= mg(0, 1))
+    ok_v = (m > mg(-1, 0)) & (m >= mg(1, 0))
+    ok_d = np.where(same_sign, (m > mg(-1, -1)) & (m > mg(1, 1)), (m > mg(-1, 1)) & (m > mg(1, -1)))
+    cand = (m > low) & ((horiz & ok_h) | (vert & ok_v) | (diag & ok_d))
+    strong = cand & (m > high)
+    lab, n = ndi.label(cand, structure=np.ones((3, 3), np.uint8))
+    keep = np.zeros(n + 1, bool)
+    keep[np.unique(lab[strong])] = True
+    keep[0] = False
+    return (keep[lab] * 255).astype(np.uint8)
+
+
 # --------------------------------------------------------------------------- full unit
 def segment_cell(gray, method='otsu', gaussian_blur=3, morph_kernel=3, info: Optional[dict] = None,
                  adapt_block=51, adapt_C=10):

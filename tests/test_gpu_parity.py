@@ -168,6 +168,34 @@ def test_detect_defects(insp, cfg):
             assert rec["roi_area"] == int((info['roi'] > 0).sum())
 
 
+@pytest.mark.parametrize("cfg", [(6, 24, 20), (1, 8, 0), (0, 3, 0), (6, 100, 5), (17, 255, 0), (6, 0, 0), (3, 12, 1)])
+def test_detect_defects_canny(insp, cfg):
+    """indexing_ui.py:1536-1539: cv2.Canny inside the ROI, then the same contour filter.  Integer: bit-exact."""
+    r, thr, mn = cfg
+    rng = np.random.default_rng(19)
+    cases = []
+    for gray in crops(2, seed0=700):
+        cases.append((gray, R.segment_cell(gray)))
+    g = rng.integers(0, 256, size=(96, 96), dtype=np.uint8)
+    cases.append((g, np.full((96, 96), 255, np.uint8)))                    # noise: tens of thousands of edge runs
+    g1 = cv2.GaussianBlur(rng.integers(0, 256, size=(200, 210), dtype=np.uint8), (7, 7), 0)
+    cases.append((g1, np.full(g1.shape, 255, np.uint8)))
+    g2 = rng.integers(0, 256, size=(315, 316), dtype=np.uint8)
+    cases.append((g2, np.full(g2.shape, 255, np.uint8)))                   # run table overflows shared memory
+    g3 = rng.integers(0, 256, size=(5, 7), dtype=np.uint8)
+    cases.append((g3, np.full(g3.shape, 255, np.uint8)))
+    p = vi_b200.default_params(defect_method='canny', threshold=thr, min_area=mn, erode_px=r)
+    for gray, seg in cases:
+        info = {}
+        ref = R.detect_defects(gray, seg, 'canny', thr, mn, r, info)
+        got, rec = insp.detect_defects(gray, seg, p, return_record=True)
+        assert (ref is None) == (got is None), (cfg, gray.shape)
+        if ref is not None:
+            assert np.array_equal(got, ref), (cfg, gray.shape, int((got != ref).sum()))
+            assert rec["defect_area"] == int((ref > 0).sum())
+            assert rec["n_kept"] == info["n_kept"]
+
+
 def _run_batch(insp, g, fi, params, is_reference, refc, exclusions, host=False, labels=False):
     import torch
     grid = Grid(boxes=g.boxes, exclusions=exclusions, ref_centroids=refc or {})
@@ -219,7 +247,7 @@ def test_segment_cell_adaptive(insp):
     assert bad <= 1e-4 * tot, (bad, tot)
 
 
-@pytest.mark.parametrize("name", ["config1", "config4", "config5", "blur5_morph5", "adaptive"])
+@pytest.mark.parametrize("name", ["config1", "config4", "config5", "blur5_morph5", "adaptive", "canny"])
 def test_batch_matches_reference_goldens(insp, golden, name):
     g = golden(name)
     meta = g.meta
@@ -312,7 +340,9 @@ def test_error_paths(insp):
         seg.fill_internal_holes(np.zeros((2, 2, 2), np.uint8))
     assert seg.mask_stats(np.zeros((4, 4), np.uint8)) == {'area': 0, 'centroid': (0, 0)}
     with pytest.raises(vi_b200.ViError):
-        seg.detect_defects(np.zeros((8, 8), np.uint8), np.full((8, 8), 255, np.uint8), method='canny')   # not built yet: fails loudly
+        insp.segment_cell(np.zeros((8, 8), np.uint8), vi_b200.default_params(seg_method=7))             # not a reference option
+    with pytest.raises(vi_b200.ViError):
+        insp.segment_cell(np.zeros((8, 8), np.uint8), vi_b200.default_params(median_ksize=5))           # the reference hard-codes 21
     with pytest.raises(vi_b200.ViError):
         insp.set_grid([(0, 0, 2000, 2000)])                                  # does not fit shared memory
     insp.set_grid([(10, 10, 50, 50)])

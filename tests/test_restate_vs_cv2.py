@@ -75,6 +75,27 @@ def test_adaptive_taps_and_mask():
     assert bad <= 1e-4 * tot, (bad, tot)
 
 
+def test_canny_restatement_is_cv2():
+    """indexing_ui.py:1537: integer, so bit-exact; cv2's result does not depend on its thread count."""
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, size=(120, 130), dtype=np.uint8), _crops(1)[0],
+            cv2.GaussianBlur(rng.integers(0, 256, size=(200, 210), dtype=np.uint8), (7, 7), 0),
+            rng.integers(0, 256, size=(5, 7), dtype=np.uint8), np.full((9, 9), 77, np.uint8),
+            rng.integers(0, 256, size=(1, 1), dtype=np.uint8), rng.integers(0, 256, size=(1, 40), dtype=np.uint8)]
+    for thr in (24, 3, 1, 0, 100, 255, 8):
+        lo, hi = max(1, thr // 2), max(2, thr)
+        for im in imgs:
+            ref = cv2.Canny(im, lo, hi)
+            assert np.array_equal(S.canny_edges(im, lo, hi), ref), (thr, im.shape)
+    n0 = cv2.getNumThreads()
+    try:
+        cv2.setNumThreads(1)
+        one = cv2.Canny(imgs[1], 12, 24)
+    finally:
+        cv2.setNumThreads(n0)
+    assert np.array_equal(one, cv2.Canny(imgs[1], 12, 24))
+
+
 def test_otsu_matches_cv2():
     rng = np.random.default_rng(0)
     imgs = _crops(4)

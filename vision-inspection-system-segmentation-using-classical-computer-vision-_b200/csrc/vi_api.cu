@@ -345,10 +345,13 @@ static int fill_params(KArgs& a, const vi_params* p) {
         a.adapt_bs = bs;
         gaussian_taps_f32(bs, a.ataps);
     }
-    if (p->defect_method == 1) return fail(VI_ERR_UNSUPPORTED, "defect_method 'canny' (indexing_ui.py:1536-1539) is not built yet");
+    if (p->defect_method != 0 && p->defect_method != 1) return fail(VI_ERR_ARG, "defect_method %d (0 threshold, 1 canny)", p->defect_method);
     if (p->median_ksize != 21) return fail(VI_ERR_UNSUPPORTED, "median_ksize must be 21 (indexing_ui.py:1522)");
     if (p->threshold < 0 || p->threshold > 255) return fail(VI_ERR_ARG, "threshold %d outside 0..255", p->threshold);
     if (p->erode_px < 0 || p->min_area < 0) return fail(VI_ERR_ARG, "erode_px / min_area must be >= 0");
+    a.canny_low = std::max(1, p->threshold / 2);                                                          // indexing_ui.py:1537
+    a.canny_high = std::max(2, p->threshold);
+    if (a.canny_low > a.canny_high) std::swap(a.canny_low, a.canny_high);
     int k = 0;
     if (p->gaussian_blur > 0) k = (p->gaussian_blur % 2 == 1) ? p->gaussian_blur : p->gaussian_blur + 1;   // segmentation.py:79
     if (k == 1) k = 0;                                     // a 1x1 Gaussian is the identity

@@ -131,6 +131,7 @@ struct KArgs {
     int blur_k;                     // 0 skip, 3 fast path, else general (odd)
     int taps[kMaxTaps];             // 8.8 fixed-point Gaussian taps for the general path
     int se_k;                       // 0 skip, 3 = cross fast path, else general
+    int canny_low, canny_high;      // cv2.Canny thresholds max(1, thr/2), max(2, thr) (indexing_ui.py:1537)
     int adapt_bs;                   // adaptive threshold block size (odd, >= 3); used when p.seg_method == 1
     float ataps[kMaxAdapt];         // float32 Gaussian taps of the adaptive mean (cv2.getGaussianKernel(bs, 0, CV_32F))
     signed char se_lo[kMaxSE], se_hi[kMaxSE];   // per SE row: x-offset span [lo,hi] relative to the anchor (lo>hi: empty)

@@ -5,6 +5,7 @@
 #include <cmath>
 #include "vi_pipeline.cuh"
 #include "vi_rank.cuh"
+#include "vi_canny.cuh"
 
 namespace vi {
 
@@ -360,11 +361,22 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     ccl_paint(MD, nullptr, g, ws, [broot](int root) { return root == broot; });
     __syncthreads();
     pt.tick();   // 9 ROI labelling
-    // ---- P11: median residual -------------------------------------------------
     const int thr = a.p.threshold;
+    int n_amb = 0;
+    int any_resid = 0;
+    if (a.p.defect_method == 1) {
+        // ---- P11': Canny edges inside the ROI (indexing_ui.py:1536-1539) ----------------
+        canny_candidates(gray, g, a.canny_low, a.canny_high, MA, MB);
+        __syncthreads();
+        R = canny_hysteresis(sh.cs, MA, MB, MC, g, ws_s, ws_g, ws);
+        n_runs_max = max(n_runs_max, R);
+        for (int i = tid; i < g.nwords; i += kThreads) { const unsigned v = MC[i] & MD[i]; MB[i] = v; any_resid |= (v != 0); }
+        any_resid = __syncthreads_or(any_resid);
+        for (int k = 0; k < 4; ++k) pt.tick();   // 10..13 (the residual path's slots)
+    } else {
+    // ---- P11: median residual -------------------------------------------------
     select_levels(sh, npix, thr);
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
-    int n_amb;
     if (g.w <= kThreads && rank_ws_bytes(g.w) <= plan.ws_bytes) {
         RankWs rw = rank_ws_carve(WS, g.w, MA, MB, plan.mask_bytes);
         rank_tables(sh.levels, rw);
@@ -393,10 +405,10 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     // ---- P12: open with the 3x3 cross -----------------------------------------
     cross3_pass<true>(MC, MA, g); __syncthreads();
     cross3_pass<false>(MA, MB, g);
-    int any_resid = 0;
     for (int i = tid; i < g.nwords; i += kThreads) any_resid |= (MA[i] != 0);       // erosion result non-empty <=> opening non-empty
     any_resid = __syncthreads_or(any_resid);
     pt.tick();   // 13 open
+    }
     if (!any_resid) {
         // nothing survives the opening: the detector returns None (indexing_ui.py:1559-1560)
         if (def_out) zero_bytes(def_out, npix);
