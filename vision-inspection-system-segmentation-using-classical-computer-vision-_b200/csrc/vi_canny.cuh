@@ -31,7 +31,7 @@ __device__ __forceinline__ int sobel_mag_at(const uint8_t* gray, const Geom& g, 
 }
 
 // CAND = pixels that survive non-maximum suppression with m > low; STRONG = those with m > high.
-__device__ inline void canny_candidates(const uint8_t* gray, const Geom& g, int low, int high, unsigned* CAND, unsigned* STRONG) {
+VI_PHASE void canny_candidates(const uint8_t* gray, const Geom& g, int low, int high, unsigned* CAND, unsigned* STRONG) {
     const int lane = lane_id();
     for (int i = warp_id(); i < g.nwords; i += kWarps) {
         int y, c; word_rc(g, i, y, c);
@@ -63,18 +63,18 @@ __device__ inline void canny_candidates(const uint8_t* gray, const Geom& g, int 
 }
 
 // EDGES = the 8-components of CAND that hold a STRONG pixel.
-__device__ inline int canny_hysteresis(CtaScratch& cs, const unsigned* CAND, const unsigned* STRONG, unsigned* EDGES, const Geom& g,
+VI_PHASE int canny_hysteresis(CtaScratch& cs, const unsigned* CAND, const unsigned* STRONG, unsigned* EDGES, const Geom& g,
                                        const CclWs& ws_s, const CclWs& ws_g, CclWs& ws) {
     const int R = ccl_build(cs, CAND, g, true, false, ws_s, ws_g, ws);
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {
-        const int y = ws.yy[i], xs = ws.xs[i], xe = ws.xe[i];
+        const int y = ws.yy()[i], xs = ws.xs()[i], xe = ws.xe()[i];
         unsigned hit = 0;
         for (int c = xs >> 5; c <= (xe >> 5); ++c)
             hit |= STRONG[y * g.wpr + c] & bit_range(max(xs, c * 32) - c * 32, min(xe, c * 32 + 31) - c * 32);
-        if (hit) ws.acc0[ws.parent[i]] = 1u;          // every writer stores the same value
+        if (hit) ws.acc0()[ws.parent()[i]] = 1u;          // every writer stores the same value
     }
     __syncthreads();
-    const unsigned* acc0 = ws.acc0;
+    const unsigned* acc0 = ws.acc0();
     ccl_paint(EDGES, nullptr, g, ws, [acc0](int root) { return acc0[root] != 0u; });
     __syncthreads();
     return R;

@@ -20,15 +20,19 @@
 
 namespace vi {
 
+// Three words, not seven pointers: the arrays are derived from the base on use, so a workspace choice is one
+// select and nothing of it has to be held across phases.
 struct CclWs {
-    unsigned short* xs;   // [cap+1]
-    unsigned short* xe;   // [cap+1]
-    unsigned short* yy;   // [cap+1]
-    int* parent;          // [cap+1]
-    unsigned* acc0;       // [cap+1] per-root accumulator
-    unsigned* acc1;       // [cap+1] per-root accumulator
-    int* row_first;       // [h+2] first run id of each row; row_first[h] = R+1
+    unsigned char* base;
     int cap;
+    int rf;               // bytes of the row_first table
+    __device__ __forceinline__ int* row_first() const { return reinterpret_cast<int*>(base); }            // [h+2] first run id of each row; [h] = R+1
+    __device__ __forceinline__ int* parent() const { return reinterpret_cast<int*>(base + rf); }          // [cap+1]
+    __device__ __forceinline__ unsigned* acc0() const { return reinterpret_cast<unsigned*>(base + rf + (cap + 1) * 4); }   // per-root accumulator
+    __device__ __forceinline__ unsigned* acc1() const { return reinterpret_cast<unsigned*>(base + rf + (cap + 1) * 8); }   // per-root accumulator
+    __device__ __forceinline__ unsigned short* xs() const { return reinterpret_cast<unsigned short*>(base + rf + (cap + 1) * 12); }
+    __device__ __forceinline__ unsigned short* xe() const { return reinterpret_cast<unsigned short*>(base + rf + (cap + 1) * 14); }
+    __device__ __forceinline__ unsigned short* yy() const { return reinterpret_cast<unsigned short*>(base + rf + (cap + 1) * 16); }
 };
 
 __host__ __device__ inline size_t ccl_ws_bytes(int cap, int h) {
@@ -37,15 +41,7 @@ __host__ __device__ inline size_t ccl_ws_bytes(int cap, int h) {
 
 __device__ inline CclWs ccl_ws_carve(unsigned char* base, int cap, int h) {
     CclWs ws;
-    ws.row_first = reinterpret_cast<int*>(base);
-    unsigned char* p = base + align16((h + 2) * 4);
-    ws.parent = reinterpret_cast<int*>(p); p += (size_t)(cap + 1) * 4;
-    ws.acc0 = reinterpret_cast<unsigned*>(p); p += (size_t)(cap + 1) * 4;
-    ws.acc1 = reinterpret_cast<unsigned*>(p); p += (size_t)(cap + 1) * 4;
-    ws.xs = reinterpret_cast<unsigned short*>(p); p += (size_t)(cap + 1) * 2;
-    ws.xe = reinterpret_cast<unsigned short*>(p); p += (size_t)(cap + 1) * 2;
-    ws.yy = reinterpret_cast<unsigned short*>(p);
-    ws.cap = cap;
+    ws.base = base; ws.cap = cap; ws.rf = align16((h + 2) * 4);
     return ws;
 }
 
@@ -93,7 +89,7 @@ __device__ __forceinline__ void run_edges(const unsigned* M, const Geom& g, int 
 
 // Builds runs + components of mask M.  ws_s (shared) is used when the runs fit,
 // else ws_g (global scratch).  Returns R (run count) and the workspace used.
-__device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
+VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
                                 const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PhaseTimer* pt = nullptr) {
     const int per = (g.nwords + kThreads - 1) / kThreads;
     const int i0 = threadIdx.x * per;
@@ -114,63 +110,63 @@ __device__ inline int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g
         int y, c; word_rc(g, i, y, c);
         unsigned s, e;
         run_edges(M, g, y, c, s, e);
-        if (c == 0) ws.row_first[y] = (int)os + 1;
+        if (c == 0) ws.row_first()[y] = (int)os + 1;
         while (s) {
             int b = __ffs(s) - 1; s &= s - 1;
             ++os;
-            ws.xs[os] = (unsigned short)(c * 32 + b);
-            ws.yy[os] = (unsigned short)y;
+            ws.xs()[os] = (unsigned short)(c * 32 + b);
+            ws.yy()[os] = (unsigned short)y;
         }
         while (e) {
             int b = __ffs(e) - 1; e &= e - 1;
             ++oe;
-            ws.xe[oe] = (unsigned short)(c * 32 + b);
+            ws.xe()[oe] = (unsigned short)(c * 32 + b);
         }
     }
-    if (threadIdx.x == 0) { ws.row_first[g.h] = (int)R + 1; ws.parent[0] = 0; ws.acc0[0] = 0; ws.acc1[0] = 0; }
+    if (threadIdx.x == 0) { ws.row_first()[g.h] = (int)R + 1; ws.parent()[0] = 0; ws.acc0()[0] = 0; ws.acc1()[0] = 0; }
     __syncthreads();
     if (pt) pt->acc(24);
     const int c8 = conn8 ? 1 : 0;
     // A: primary link = first overlapping run of the row above
     for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
-        int y = ws.yy[i];
+        int y = ws.yy()[i];
         int link = i;
         if (y > 0) {
-            int j0 = ws.row_first[y - 1], j1 = ws.row_first[y];
-            int xs = ws.xs[i], xe = ws.xe[i];
+            int j0 = ws.row_first()[y - 1], j1 = ws.row_first()[y];
+            int xs = ws.xs()[i], xe = ws.xe()[i];
             int lo = j0, hi = j1;            // first j with xe[j] >= xs - c8
             while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if ((int)ws.xe[mid] < xs - c8) lo = mid + 1; else hi = mid;
+                if ((int)ws.xe()[mid] < xs - c8) lo = mid + 1; else hi = mid;
             }
-            if (lo < j1 && (int)ws.xs[lo] <= xe + c8) link = lo;
+            if (lo < j1 && (int)ws.xs()[lo] <= xe + c8) link = lo;
         }
-        ws.parent[i] = link;
-        ws.acc0[i] = 0;
-        ws.acc1[i] = 0;
+        ws.parent()[i] = link;
+        ws.acc0()[i] = 0;
+        ws.acc1()[i] = 0;
     }
     __syncthreads();
     if (pt) pt->acc(25);
-    ccl_jump(ws.parent, (int)R);
+    ccl_jump(ws.parent(), (int)R);
     if (pt) pt->acc(26);
     // C: remaining overlaps and the border link
     for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
-        int y = ws.yy[i];
-        int xs = ws.xs[i], xe = ws.xe[i];
+        int y = ws.yy()[i];
+        int xs = ws.xs()[i], xe = ws.xe()[i];
         if (y > 0) {
-            int j0 = ws.row_first[y - 1], j1 = ws.row_first[y];
+            int j0 = ws.row_first()[y - 1], j1 = ws.row_first()[y];
             int lo = j0, hi = j1;
             while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if ((int)ws.xe[mid] < xs - c8) lo = mid + 1; else hi = mid;
+                if ((int)ws.xe()[mid] < xs - c8) lo = mid + 1; else hi = mid;
             }
-            for (int j = lo + 1; j < j1 && (int)ws.xs[j] <= xe + c8; ++j) uf_unite(ws.parent, i, j);
+            for (int j = lo + 1; j < j1 && (int)ws.xs()[j] <= xe + c8; ++j) uf_unite(ws.parent(), i, j);
         }
-        if (border && (y == 0 || y == g.h - 1 || xs == 0 || xe == g.w - 1)) uf_unite(ws.parent, i, 0);
+        if (border && (y == 0 || y == g.h - 1 || xs == 0 || xe == g.w - 1)) uf_unite(ws.parent(), i, 0);
     }
     __syncthreads();
     if (pt) pt->acc(27);
-    ccl_jump(ws.parent, (int)R);
+    ccl_jump(ws.parent(), (int)R);
     if (pt) pt->acc(28);
     return (int)R;
 }
@@ -200,22 +196,22 @@ __device__ __forceinline__ void agg_min(unsigned* acc, bool valid, int root, uns
 // dst[word] = OR of the spans of all runs of that row whose root satisfies pred,
 // optionally OR-ed with `base` (may be null).  Word-parallel, no atomics.
 template <class Pred>
-__device__ inline void ccl_paint(unsigned* dst, const unsigned* base, const Geom& g, const CclWs& ws, Pred pred) {
+VI_PHASE void ccl_paint(unsigned* dst, const unsigned* base, const Geom& g, const CclWs& ws, Pred pred) {
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
         int y, c; word_rc(g, i, y, c);
         int x0 = c * 32, x1 = x0 + 31;
-        int j0 = ws.row_first[y], j1 = ws.row_first[y + 1];
+        int j0 = ws.row_first()[y], j1 = ws.row_first()[y + 1];
         int lo = j0, hi = j1;                 // first run with xe >= x0
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            if ((int)ws.xe[mid] < x0) lo = mid + 1; else hi = mid;
+            if ((int)ws.xe()[mid] < x0) lo = mid + 1; else hi = mid;
         }
         unsigned bits = 0;
         for (int j = lo; j < j1; ++j) {
-            int xs = ws.xs[j];
+            int xs = ws.xs()[j];
             if (xs > x1) break;
-            if (pred(ws.parent[j])) {
-                int xe = ws.xe[j];
+            if (pred(ws.parent()[j])) {
+                int xe = ws.xe()[j];
                 bits |= bit_range(max(xs, x0) - x0, min(xe, x1) - x0);
             }
         }
@@ -230,7 +226,7 @@ __device__ inline void ccl_paint(unsigned* dst, const unsigned* base, const Geom
 // Largest component (max area; ties -> smallest 2x2-block key, i.e. OpenCV's label
 // order).  Returns the root id (0 if there is no run) and its area /
 // coordinate sums through the out-params.  Uses acc0 = area, acc1 = min block key.
-__device__ inline int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
+VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
                                   unsigned& area, unsigned long long& sum_x, unsigned long long& sum_y) {
     area = 0; sum_x = 0; sum_y = 0;
     if (R == 0) return 0;
@@ -238,46 +234,46 @@ __device__ inline int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws
     for (int base = 0; base < Rpad; base += kThreads) {
         int i = base + threadIdx.x + 1;
         bool valid = i <= R;
-        int root = valid ? ws.parent[i] : 0;
-        unsigned len = valid ? (unsigned)(ws.xe[i] - ws.xs[i] + 1) : 0u;
-        agg_add(ws.acc0, valid, root, len);
+        int root = valid ? ws.parent()[i] : 0;
+        unsigned len = valid ? (unsigned)(ws.xe()[i] - ws.xs()[i] + 1) : 0u;
+        agg_add(ws.acc0(), valid, root, len);
     }
     __syncthreads();
     unsigned long long best = 0;
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
-        if (ws.parent[i] == i) {
-            unsigned long long a = ws.acc0[i];
+        if (ws.parent()[i] == i) {
+            unsigned long long a = ws.acc0()[i];
             best = a > best ? a : best;
         }
     unsigned amax = (unsigned)cta_max_u64(cs, best);
     // min block key among the components of maximal area
     const int w2 = (g.w + 1) / 2;
-    for (int i = 1 + threadIdx.x; i <= R; i += kThreads) ws.acc1[i] = 0xffffffffu;
+    for (int i = 1 + threadIdx.x; i <= R; i += kThreads) ws.acc1()[i] = 0xffffffffu;
     __syncthreads();
     for (int base = 0; base < Rpad; base += kThreads) {
         int i = base + threadIdx.x + 1;
         bool valid = i <= R;
-        int root = valid ? ws.parent[i] : 0;
-        valid = valid && ws.acc0[root] == amax;
-        unsigned key = valid ? (unsigned)((ws.yy[i] >> 1) * w2 + (ws.xs[i] >> 1)) : 0xffffffffu;
-        agg_min(ws.acc1, valid, root, key);
+        int root = valid ? ws.parent()[i] : 0;
+        valid = valid && ws.acc0()[root] == amax;
+        unsigned key = valid ? (unsigned)((ws.yy()[i] >> 1) * w2 + (ws.xs()[i] >> 1)) : 0xffffffffu;
+        agg_min(ws.acc1(), valid, root, key);
     }
     __syncthreads();
     unsigned long long sel = 0;   // pick (min key) -> encode as max of (~key, root)
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
-        if (ws.parent[i] == i && ws.acc0[i] == amax) {
-            unsigned long long v = ((unsigned long long)(0xffffffffu - ws.acc1[i]) << 32) | (unsigned)i;
+        if (ws.parent()[i] == i && ws.acc0()[i] == amax) {
+            unsigned long long v = ((unsigned long long)(0xffffffffu - ws.acc1()[i]) << 32) | (unsigned)i;
             sel = v > sel ? v : sel;
         }
     sel = cta_max_u64(cs, sel);
     int broot = (int)(sel & 0xffffffffu);
     unsigned long long sx = 0, sy = 0;
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
-        if (ws.parent[i] == broot) {
-            unsigned long long xs = ws.xs[i], xe = ws.xe[i];
+        if (ws.parent()[i] == broot) {
+            unsigned long long xs = ws.xs()[i], xe = ws.xe()[i];
             unsigned long long len = xe - xs + 1;
             sx += (xs + xe) * len / 2;
-            sy += (unsigned long long)ws.yy[i] * len;
+            sy += (unsigned long long)ws.yy()[i] * len;
         }
     sum_x = cta_sum_u64(cs, sx);
     sum_y = cta_sum_u64(cs, sy);

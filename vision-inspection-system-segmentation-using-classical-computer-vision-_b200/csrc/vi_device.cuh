@@ -12,6 +12,10 @@
 
 namespace vi {
 
+// Pipeline phases.  (Compiling them as __noinline__ functions of their own was measured: reference
+// arguments then live in local memory and the labelling phases ran 2-3x slower.)
+#define VI_PHASE __device__ inline
+
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kHistWords = 2048;   // per-warp lane-private histogram: [64 bin-quads][32 lanes] u32, 4 x 8-bit counters
@@ -21,9 +25,6 @@ constexpr int kMaxTaps = 33;
 constexpr int kMaxSE = 33;
 constexpr int kMaxAdapt = 201;      // widest adaptive-threshold block (the reference's widget range, indexing_ui.py:805)
 constexpr int kLevels = 6;         // rank-count levels of the median stage (two words of three 10-bit fields)
-constexpr int kBandRows = 16;      // output rows per band of the rank-count stage
-constexpr int kSegL = 11;         // columns per lane in the horizontal prefix of the rank-count stage
-constexpr int kRankMaxW = 32 * kSegL - 20;   // widest unit the one-warp-per-row pass covers (332)
 constexpr int kNumMasks = 5;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -87,8 +88,9 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     p->mask_bytes = align16(g.nwords * 4);
     p->band_pitch = 0;
     // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
-    int rpitch = (wmax + 3) & ~3;
-    int band = wmax <= kThreads ? 2 * 256 * 4 + 8 * rpitch * 4 + 16 * rpitch * 8 + 64 : 0;
+    int cpitch = ((wmax + 2) / 3 + 2) & ~1;
+    int rch = wmax <= 96 ? 3 : wmax <= 224 ? 7 : wmax <= 352 ? 11 : 15;
+    int band = wmax <= 480 ? 16 * (32 * rch + 2) * 8 + 32 * cpitch * 2 + 64 * 4 + 64 : 0;   // vi_rank.cuh: rank_ws_bytes
     int otsu = 256 * 8 * 6 + 256;
     int rowfirst = align16((hmax + 2) * 4);
     int want_cap = 2048;
@@ -166,17 +168,24 @@ struct CtaScratch {
 // Diagnostics: per-phase SM cycle counts of one unit (thread 0, after the barrier
 // that ends the phase), written only when KArgs::prof is set.
 constexpr int kProfSlots = 32;
+struct PtState { long long* out; long long t; int k; int pad; };      // lives in shared memory: no registers held across phases
 struct PhaseTimer {
-    long long* out;
-    long long t;
-    int k;
-    __device__ __forceinline__ void start(long long* o) { out = o; k = 0; if (out && threadIdx.x == 0) t = clock64(); }
+    PtState* s;
+    __device__ __forceinline__ void start(PtState* st, long long* o) {
+        s = st;
+        if (threadIdx.x == 0) { s->out = o; s->k = 0; if (o) s->t = clock64(); }
+    }
     __device__ __forceinline__ void tick() {
-        if (out && threadIdx.x == 0) { long long n = clock64(); if (k < kProfSlots) out[k] += n - t; ++k; t = n; }
+        if (threadIdx.x == 0 && s->out) {
+            const long long n = clock64();
+            const int k = s->k;
+            if (k < kProfSlots) s->out[k] += n - s->t;
+            s->k = k + 1; s->t = n;
+        }
     }
     // sub-phase accounting: add the time since the last tick/acc to `slot` without consuming a phase slot
     __device__ __forceinline__ void acc(int slot) {
-        if (out && threadIdx.x == 0) { long long n = clock64(); out[slot] += n - t; t = n; }
+        if (threadIdx.x == 0 && s->out) { const long long n = clock64(); s->out[slot] += n - s->t; s->t = n; }
     }
 };
 
@@ -302,7 +311,7 @@ __device__ __forceinline__ unsigned bit_range(int a, int b) {
 // One pass of a 3x3-cross erosion (out-of-crop = 1) or dilation (out-of-crop = 0):
 // cv2.getStructuringElement(MORPH_ELLIPSE,(3,3)) is the cross.
 template <bool ERODE>
-__device__ inline void cross3_pass(const unsigned* src, unsigned* dst, const Geom& g) {
+VI_PHASE void cross3_pass(const unsigned* src, unsigned* dst, const Geom& g) {
     const unsigned fill = ERODE ? 0xffffffffu : 0u;
     const unsigned pad = fill & ~g.lastmask;             // padding bits of a row's last word read as `fill`
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
@@ -323,7 +332,7 @@ __device__ inline void cross3_pass(const unsigned* src, unsigned* dst, const Geo
 // segmentation.py:93).  erode: AND over offsets, outside = 1; dilate: OR over the
 // same (un-reflected) offsets, outside = 0.
 template <bool ERODE>
-__device__ inline void se_pass(const unsigned* src, unsigned* dst, const Geom& g, int k,
+VI_PHASE void se_pass(const unsigned* src, unsigned* dst, const Geom& g, int k,
                                const signed char* lo, const signed char* hi) {
     const unsigned fill = ERODE ? 0xffffffffu : 0u;
     const int a = k / 2;
@@ -359,7 +368,7 @@ __device__ __forceinline__ unsigned mword_shift_rep(const unsigned* M, const Geo
 // buffer that holds the result.  `src` must not be bufA or bufB's partner in use.
 constexpr int kErodeDirectMax = 10;     // radii up to this take one direct pass per axis
 
-__device__ inline unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsigned* bufB, const Geom& g, int r) {
+VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsigned* bufB, const Geom& g, int r) {
     const unsigned* cur = src;
     unsigned* nxt = (src == bufA) ? bufB : bufA;
     if (r <= kErodeDirectMax) {

@@ -22,11 +22,19 @@
 //    Exact for any level set and any image
 //    (oracle/restate.py: residual_mask_lattice is the numpy twin).
 //
-// Box sums are separable.  V: one thread per column accumulates 3-row block sums
-// (a lattice row's 21-row window is exactly 7 blocks); a ring of packed block sums
-// gives the sliding 7-block sum.  H: one warp per lattice row, one lane per cell:
-// 3-column triple sums (10 replicated columns each side), a warp scan, and the
-// cell's 21-column window is P[i+6] - P[i-1].
+// Box sums are separable and every stage below is a straight-line pass:
+//   V   one thread per column (whole cells per warp, spread over all warps) walks down the
+//       rows in 3-row blocks: B(b) = sum of the packed level indicators of the
+//       block (field-parallel arithmetic, no table), S(j) = sum of blocks j-3..j+3 (the
+//       21-row window of lattice row j) kept by a ring of packed block sums, and
+//       the block's gray min / max reduced over the cell's 3 columns by two
+//       shuffles (min and 255-max packed as 16-bit halves: one VIMNMX3 does both).
+//   S   one warp per lattice row turns S(j, x) into an inclusive prefix over x
+//       (11 columns per lane, one warp scan; packed fields may wrap, differences
+//       of prefixes are exact because every 21-column sum is < 1024).
+//   C   one lane per cell: window = P[x+10] - P[x-11] (+ replicated edge columns),
+//       two field-parallel compares give the bracket, a 49-entry table the four
+//       byte thresholds, and the cell min / max decide clean or dirty.
 #pragma once
 #include "vi_device.cuh"
 
@@ -34,54 +42,65 @@ namespace vi {
 
 constexpr int kCell = 3;
 constexpr int kLatBand = 16;             // lattice rows per band (= warps per CTA)
-constexpr int kCellsPerPass = 26;        // 32 triples per pass, 6 of them look-ahead
-constexpr int kPassBatch = 5;            // passes interleaved per lattice row (5 x 26 cells = 390 px)
+constexpr int kColsPerWarp = 30;         // V pass: 10 whole cells per warp
+constexpr int kRankMaxW = kWarps * kColsPerWarp;      // widest unit of the lattice pass (480)
+constexpr int kCmmRows = 2 * kLatBand;    // cell min/max rows: two band buffers (a band also writes the next band's first 3 rows)
 constexpr unsigned kFld = 0x00300C03u;   // 2-bit block-sum fields at the 10-bit field positions
 constexpr unsigned kFlag = 0x20080200u;  // bit 9 of each 10-bit field
 constexpr unsigned kGe263 = 249u | (249u << 10) | (249u << 20);   // field + 249 >= 512  <=>  field >= 263
 constexpr unsigned kGe179 = 333u | (333u << 10) | (333u << 20);   // field + 333 >= 512  <=>  field >= 179
 
 struct RankWs {
-    unsigned* lut0;     // [256] indicators of levels 0..2 (10-bit fields)
-    unsigned* lut1;     // [256] indicators of levels 3..5
-    unsigned* ring;     // [8][pitch] packed 3-row block sums
-    uint2* cs;          // [kLatBand][pitch] 7-block column sums
+    uint2* cs;          // [kLatBand][P] (0, then per column) 7-block column sums, then their prefix over x
+    unsigned short* cmm;// [2][kLatBand][cpitch] cell gray min | (255 - max) << 8
+    unsigned* table;    // [49] thresholds U1 | U2 << 8 | U3 << 16 | U4 << 24 by (n179, n263)
     uint2* dirty;       // [dirty_cap] (cell position, thresholds); more are classified inline
     unsigned* exact;    // [exact_cap] ambiguous pixels (y << 16 | x); more are counted inline
     int dirty_cap, exact_cap;
     int* counters;      // [0] dirty cells, [1] ambiguous pixels listed, [2] ambiguous pixels total
-    int pitch;
+    int P, cpitch;
 };
 
+// Columns per lane of the prefix pass (odd: a lane's chunk starts land on distinct banks) and the row pitch of
+// cs in uint2: one leading zero (the prefix "before column 0") + 32 * CH columns + one dummy column (written by
+// the V lanes that own no column), so no access needs a bounds test (a prefix only flows forward: what lies
+// past column w-1 is never read back).
+__host__ __device__ inline int rank_ch(int w) { return w <= 96 ? 3 : w <= 224 ? 7 : w <= 352 ? 11 : 15; }
+__host__ __device__ inline int rank_P(int w) { return 32 * rank_ch(w) + 2; }
+__host__ __device__ inline int rank_cpitch(int w) { return ((w + kCell - 1) / kCell + 2) & ~1; }      // cells + a dummy slot
 __host__ __device__ inline int rank_ws_bytes(int w) {
-    const int pitch = (w + 3) & ~3;
-    return 2 * 256 * 4 + 8 * pitch * 4 + kLatBand * pitch * 8 + 64;
+    return kLatBand * rank_P(w) * 8 + kCmmRows * rank_cpitch(w) * 2 + 64 * 4 + 64;
 }
 
 // The two lists live in two mask buffers that are idle during this stage.
 __device__ inline RankWs rank_ws_carve(unsigned char* base, int w, unsigned* listA, unsigned* listB, int mask_bytes) {
     RankWs r;
-    r.pitch = (w + 3) & ~3;
-    r.cs = reinterpret_cast<uint2*>(base); base += kLatBand * r.pitch * 8;
+    r.P = rank_P(w); r.cpitch = rank_cpitch(w);
+    r.cs = reinterpret_cast<uint2*>(base); base += kLatBand * r.P * 8;
+    r.cmm = reinterpret_cast<unsigned short*>(base); base += kCmmRows * r.cpitch * 2;
+    r.table = reinterpret_cast<unsigned*>(base); base += 64 * 4;
+    r.counters = reinterpret_cast<int*>(base);
     r.dirty = reinterpret_cast<uint2*>(listA); r.dirty_cap = mask_bytes / 8;
     r.exact = listB; r.exact_cap = mask_bytes / 4;
-    r.lut0 = reinterpret_cast<unsigned*>(base); base += 256 * 4;
-    r.lut1 = reinterpret_cast<unsigned*>(base); base += 256 * 4;
-    r.ring = reinterpret_cast<unsigned*>(base); base += 8 * r.pitch * 4;
-    r.counters = reinterpret_cast<int*>(base);
     return r;
 }
 
-__device__ inline void rank_tables(const int* lv, RankWs w) {
+VI_PHASE void rank_tables(const int* lv, int thr, RankWs w) {
     const int v = threadIdx.x;
-    if (v < 256) {
-        unsigned lo = 0, hi = 0;
-        for (int k = 0; k < 3; ++k) lo |= (unsigned)(v <= lv[k]) << (10 * k);
-        for (int k = 0; k < 3; ++k) hi |= (unsigned)(v <= lv[3 + k]) << (10 * k);
-        w.lut0[v] = lo;
-        w.lut1[v] = hi;
+    if (v >= 256 && v < 256 + 49) {
+        const int e = v - 256, n179 = e / 7, n263 = e - n179 * 7;
+        const int lo_idx = kLevels - n179;        // levels 0..lo_idx-1 surely have C <= 220: med >  LO
+        const int hi_idx = kLevels - n263;        // level hi_idx surely has C >= 221:        med <= HI
+        const int LO = lo_idx > 0 ? lv[lo_idx - 1] : -1;
+        const int HI = hi_idx < kLevels ? lv[hi_idx] : 255;
+        const int U1 = min(max(LO - thr + 1, 0), 255);     // defect if g <  U1
+        const int U4 = min(HI + thr, 255);                 // defect if g >  U4
+        const int U2 = max(HI - thr, 0);                   // clean needs g >= U2
+        const int U3 = min(LO + thr + 1, 255);             // clean needs g <= U3
+        w.table[e] = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
     }
-    if (v < 4) w.counters[v] = 0;
+    if (v >= 320 && v < 324) w.counters[v - 320] = 0;
+    if (v >= 352 && v < 352 + kLatBand) w.cs[(v - 352) * w.P] = make_uint2(0u, 0u);      // the prefix before column 0
 }
 
 // Exact decision for one pixel: #(window <= g+thr) <= 220 or #(window <= g-thr-1) >= 221.
@@ -127,135 +146,201 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
     }
 }
 
+// gray q as (q, 255 - q) 16-bit halves: the packed minimum carries min and 255 - max.
+__device__ __forceinline__ unsigned mm_pack(unsigned q) { return q * 0xFFFF0001u + 0x00FF0000u; }
+
+// S + C for one lattice row (one warp).  CH = columns per lane of the prefix pass (odd).
+template <int CH>
+__device__ __forceinline__ void rank_row_cells(const uint8_t* gray, const Geom& g, RankWs& w, uint2* row,
+                                               const unsigned short* cm, int cj, int nlx, int thr, const unsigned* ROI,
+                                               unsigned* CAND) {
+    const int lane = lane_id();
+    const int wm1 = g.w - 1;
+    {   // ---- S: inclusive prefix over the row ---------------------------------------
+        uint2* chunk = row + lane * CH;
+        uint2 v[CH];
+        unsigned a0 = 0, a1 = 0;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const uint2 t = chunk[k];
+            a0 += t.x; a1 += t.y;
+            v[k] = make_uint2(a0, a1);
+        }
+        unsigned e0 = a0, e1 = a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y0 = __shfl_up_sync(kFull, e0, o), y1 = __shfl_up_sync(kFull, e1, o);
+            if (lane >= o) { e0 += y0; e1 += y1; }
+        }
+        e0 -= a0; e1 -= a1;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) chunk[k] = make_uint2(v[k].x + e0, v[k].y + e1);
+    }
+    __syncwarp();
+    // ---- C: one lane per cell -------------------------------------------------------
+    const uint2 first = row[0];
+    uint2 last = row[wm1];
+    { const uint2 l2 = row[wm1 - 1]; last.x -= l2.x; last.y -= l2.y; }
+    for (int i0 = 0; i0 < nlx; i0 += 32) {
+        const int i = min(i0 + lane, nlx - 1);                       // surplus lanes repeat the last cell
+        const int a = kCell * i - 9, b = kCell * i + 11;            // window columns (clamped to the crop)
+        const uint2 hi = row[min(b, wm1)], lo = row[max(a, 0) - 1];
+        const unsigned nl = (unsigned)max(-a, 0), nr = (unsigned)max(b - wm1, 0);      // replicated edge columns
+        const unsigned C0 = hi.x - lo.x + nl * first.x + nr * last.x;
+        const unsigned C1 = hi.y - lo.y + nl * first.y + nr * last.y;
+        const int n263 = __popc((C0 + kGe263) & kFlag) + __popc((C1 + kGe263) & kFlag);
+        const int n179 = __popc((C0 + kGe179) & kFlag) + __popc((C1 + kGe179) & kFlag);
+        const unsigned cw = w.table[n179 * 7 + n263];
+        const unsigned mmv = cm[i];
+        const unsigned mn = mmv & 255u, mx = 255u - (mmv >> 8);
+        const bool dirty = (i0 + lane < nlx) && (mn < ((cw >> 8) & 255u) || mx > ((cw >> 16) & 255u));
+    // append the dirty cells (one atomic per warp)
+        const unsigned dm = __ballot_sync(kFull, dirty);
+        if (dm) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
+            base = __shfl_sync(kFull, base, 0);
+            if (dirty) {
+                const int slot = base + __popc(dm & ((1u << lane) - 1u));
+                if (slot < w.dirty_cap) w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)i, cw);
+                else rank_dirty_cell(gray, g, thr, ROI, CAND, w, i, cj, cw);
+            }
+        }
+    }
+}
+
+// One 3-row block of one column: packed level counts of the block and its gray (min, 255 - max).
+struct VBlk { unsigned B0, B1, mm; };
+
+// Level indicators without a table (table loads with data-dependent addresses were bank-conflict bound):
+// with R = 1 | 1<<10 | 1<<20 and T = sum_k (lv_k + 512) << 10k, field k of T - q*R is lv_k + 512 - q in
+// [257, 766], so its bit 9 is (q <= lv_k).  The three pixels' bits are added by a full adder on whole words.
+constexpr unsigned kRep = 0x00100401u;
+constexpr unsigned kBit9 = 0x20080200u;
+
+__device__ __forceinline__ unsigned ind3(unsigned T, unsigned q0, unsigned q1, unsigned q2) {
+    const unsigned a = T - q0 * kRep, b = T - q1 * kRep, c = T - q2 * kRep;
+    const unsigned lo = (a ^ b ^ c) & kBit9, hi = ((a & b) | (c & (a | b))) & kBit9;
+    return (lo + 2 * hi) >> 9;
+}
+
+__device__ __forceinline__ VBlk v_block(unsigned T0, unsigned T1, unsigned q0, unsigned q1, unsigned q2) {
+    VBlk r;
+    r.B0 = ind3(T0, q0, q1, q2);
+    r.B1 = ind3(T1, q0, q1, q2);
+    const unsigned mn = __vimin3_u32(q0, q1, q2), mx = __vimax3_u32(q0, q1, q2);
+    r.mm = mn + ((255u - mx) << 16);
+    return r;
+}
+
+// Min / max of a cell's 3 columns (lanes 3c, 3c+1, 3c+2 of the warp), as min | (255 - max) << 8.
+__device__ __forceinline__ unsigned short cell_mm(unsigned mm) {
+    const unsigned m1 = __shfl_down_sync(kFull, mm, 1), m2 = __shfl_down_sync(kFull, mm, 2);
+    mm = __vimin3_u16x2(mm, m1, m2);
+    return (unsigned short)((mm & 0xFFu) | (mm >> 8));
+}
+
+// Column state of the V pass: the sliding 7-block sums and the ring of the last 8 block sums
+// (registers: the band loop is unrolled so every ring index is static).
+struct VState {
+    unsigned S0, S1;
+    unsigned r0[8], r1[8];
+    unsigned q0, q1, q2;       // gray of the next block, loaded one block ahead
+};
+
+// Blocks of one band: lattice rows j0 .. j0+15 <-> blocks b = j0+3 .. j0+18 (sequence n = b+3, ring slot n & 7).
+template <bool CLAMP>
+__device__ __forceinline__ void v_band(VState& st, unsigned T0, unsigned T1, const uint8_t* gcol, int gp, int hm1, int j0,
+                                       uint2* csp, int P, unsigned short* cmA, unsigned short* cmB, int cpitch) {
+    // every stride is an opaque register (the compiler otherwise re-derives them from the unit width per store)
+    const uint8_t* pr = gcol + (kCell * (j0 + 4)) * gp;            // rows of block j0+4 (the first prefetch)
+    int rn = kCell * (j0 + 4);
+    unsigned short* cmp = cmA + 3 * cpitch;
+#pragma unroll
+    for (int u = 0; u < kLatBand; ++u) {
+        const VBlk k = v_block(T0, T1, st.q0, st.q1, st.q2);        // block b = j0+3+u
+        if (CLAMP) {
+            st.q0 = gcol[min(rn, hm1) * gp]; st.q1 = gcol[min(rn + 1, hm1) * gp]; st.q2 = gcol[min(rn + 2, hm1) * gp];
+            rn += kCell;
+        } else {
+            st.q0 = pr[0]; st.q1 = pr[gp]; st.q2 = pr[2 * gp];
+            pr += kCell * gp;
+        }
+        *cmp = cell_mm(k.mm);                                       // lanes that lead no cell write a dummy slot
+        cmp += cpitch;
+        if (u == 12) cmp = cmB;
+        const int slot = (6 + u) & 7, old = (7 + u) & 7;
+        st.S0 += k.B0 - st.r0[old]; st.S1 += k.B1 - st.r1[old];
+        st.r0[slot] = k.B0; st.r1[slot] = k.B1;
+        *csp = make_uint2(st.S0, st.S1);                            // lanes without a column write the dummy column
+        csp += P;
+    }
+}
+
 // CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
 // Returns the number of pixels that needed an exact rank count.
-__device__ inline int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom& g, RankWs w, const int* lv,
+VI_PHASE int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom& g, RankWs w, const int* lv,
                                          int thr, const unsigned* ROI, unsigned* CAND, PhaseTimer& pt) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const int nly = (g.h + kCell - 1) / kCell, nlx = (g.w + kCell - 1) / kCell;
-    const int ntrip = nlx + 6;
-    const int wm1 = g.w - 1, hm1 = g.h - 1;
-    const bool vact = tid < g.w;
-    const int vx = vact ? tid : 0;
-    const uint8_t* gcol = gray + vx;
-    unsigned S0 = 0, S1 = 0;
-    int b = -3;                                     // next 3-row block of this column
-    // gray bytes of block b, loaded one block ahead so the table loads never wait on them
-    unsigned q0 = gcol[0], q1 = q0, q2 = q0;
-    for (int j0 = 0; j0 < nly; j0 += kLatBand) {
+    const int hm1 = g.h - 1, wm1 = g.w - 1;
+    // V: the first 3*cpw lanes of warp v own columns 3*cpw*v .. (cpw whole cells); columns past the
+    // crop edge re-read the edge column (duplicates never change a cell's min / max)
+    const int cpw = kColsPerWarp / kCell;                    // cells per warp: full warps (the pass is issue / smem-pipe bound)
+    const int vcol = warp * cpw * kCell + lane;
+    const bool vact = lane < cpw * kCell && vcol < g.w;
+    const bool vwarp = warp * cpw * kCell < g.w;               // warps without a column skip the pass
+    const uint8_t* gcol = gray + min(vcol, g.w - 1);
+    const int vcell = warp * cpw + lane / kCell;
+    const bool cell_lead = vact && (lane % kCell) == 0;
+    const int bufrows = kLatBand * w.cpitch;
+    VState st;
+    const unsigned T0 = (unsigned)(lv[0] + 512) | ((unsigned)(lv[1] + 512) << 10) | ((unsigned)(lv[2] + 512) << 20);
+    const unsigned T1 = (unsigned)(lv[3] + 512) | ((unsigned)(lv[4] + 512) << 10) | ((unsigned)(lv[5] + 512) << 20);
+    if (vwarp) {
+        // prologue: blocks b = -3 .. 2 (rows above the crop replicate row 0)
+        const int gp = g.gp;
+        const unsigned g0 = gcol[0];
+        const VBlk ka = v_block(T0, T1, g0, g0, g0);
+        st.S0 = 3 * ka.B0; st.S1 = 3 * ka.B1;
+        st.r0[0] = st.r0[1] = st.r0[2] = ka.B0; st.r1[0] = st.r1[1] = st.r1[2] = ka.B1;
+        st.r0[6] = st.r0[7] = 0; st.r1[6] = st.r1[7] = 0;
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) {
+            const VBlk k = v_block(T0, T1, gcol[min(3 * bb, hm1) * gp], gcol[min(3 * bb + 1, hm1) * gp], gcol[min(3 * bb + 2, hm1) * gp]);
+            st.S0 += k.B0; st.S1 += k.B1;
+            st.r0[3 + bb] = k.B0; st.r1[3 + bb] = k.B1;
+            const unsigned short cm = cell_mm(k.mm);
+            w.cmm[bb * w.cpitch + (cell_lead ? vcell : w.cpitch - 1)] = cm;
+        }
+        st.q0 = gcol[min(9, hm1) * gp]; st.q1 = gcol[min(10, hm1) * gp]; st.q2 = gcol[min(11, hm1) * gp];
+    }
+    int P = w.P, cpitch = w.cpitch, gp = g.gp;
+    asm volatile("" : "+r"(P), "+r"(cpitch), "+r"(gp));
+    const int csx = vact ? 1 + vcol : P - 1;                  // column slot (dummy for lanes without a column)
+    const int cmx = cell_lead ? vcell : cpitch - 1;           // cell slot (dummy for lanes that lead no cell)
+    int par = 0;
+    for (int j0 = 0; j0 < nly; j0 += kLatBand, par ^= 1) {
         const int j1 = min(j0 + kLatBand, nly);
-        // ---- V: this column's blocks up to j1+2 ------------------------------------
-        if (vact) {
-            for (; b < j1 + 3; ++b) {
-                const unsigned B0 = w.lut0[q0] + w.lut0[q1] + w.lut0[q2];
-                const unsigned B1 = w.lut1[q0] + w.lut1[q1] + w.lut1[q2];
-                const int rn = kCell * (b + 1);
-                if (rn >= 0 && rn + 2 <= hm1) {                 // interior block: no clamping
-                    const uint8_t* pr = gcol + rn * g.gp;
-                    q0 = pr[0]; q1 = pr[g.gp]; q2 = pr[2 * g.gp];
-                } else {
-                    q0 = gcol[min(max(rn, 0), hm1) * g.gp];
-                    q1 = gcol[min(max(rn + 1, 0), hm1) * g.gp];
-                    q2 = gcol[min(max(rn + 2, 0), hm1) * g.gp];
-                }
-                const unsigned o = w.ring[((b + 1) & 7) * w.pitch + vx];
-                S0 += B0; S1 += B1;
-                if (b >= 4) { S0 -= o & kFld; S1 -= (o >> 2) & kFld; }
-                w.ring[(b & 7) * w.pitch + vx] = B0 | (B1 << 2);
-                if (b >= 3) w.cs[(b - 3 - j0) * w.pitch + vx] = make_uint2(S0, S1);
-            }
+        // ---- V: blocks j0+3 .. j0+18 of every column -----------------------------------
+        if (vwarp) {
+            unsigned short* cmA = w.cmm + par * bufrows + cmx;
+            unsigned short* cmB = w.cmm + (par ^ 1) * bufrows + cmx;
+            if (kCell * (j0 + kLatBand + 3) + 2 <= hm1)
+                v_band<false>(st, T0, T1, gcol, gp, hm1, j0, w.cs + csx, P, cmA, cmB, cpitch);
+            else
+                v_band<true>(st, T0, T1, gcol, gp, hm1, j0, w.cs + csx, P, cmA, cmB, cpitch);
         }
         __syncthreads();
         pt.acc(20);
-        // ---- H: one warp per lattice row, one lane per cell --------------------------
+        // ---- S + C: one warp per lattice row ------------------------------------------
         for (int jj = warp; jj < j1 - j0; jj += kWarps) {
-            const uint2* row = w.cs + jj * w.pitch;
-            const int cj = j0 + jj;
-            // kPassBatch passes are independent: their loads and scans are interleaved for ILP
-            for (int kb = 0; kb < nlx; kb += kCellsPerPass * kPassBatch) {
-                unsigned p0[kPassBatch], p1[kPassBatch];
-#pragma unroll
-                for (int u = 0; u < kPassBatch; ++u) {
-                    // triple k covers extended columns 3k+1..3k+3  <->  columns clamp(3k-9 .. 3k-7)
-                    const int k = kb + u * kCellsPerPass + lane;
-                    p0[u] = 0; p1[u] = 0;
-                    if (k < ntrip && kb + u * kCellsPerPass < nlx) {
-                        const int c0 = kCell * k - 9;
-                        const uint2 a = row[min(max(c0, 0), wm1)], bb = row[min(max(c0 + 1, 0), wm1)],
-                                    c = row[min(max(c0 + 2, 0), wm1)];
-                        p0[u] = a.x + bb.x + c.x; p1[u] = a.y + bb.y + c.y;
-                    }
-                }
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                    for (int u = 0; u < kPassBatch; ++u) {
-                        const unsigned x0 = __shfl_up_sync(kFull, p0[u], o), x1 = __shfl_up_sync(kFull, p1[u], o);
-                        if (lane >= o) { p0[u] += x0; p1[u] += x1; }
-                    }
-                }
-                unsigned C0[kPassBatch], C1[kPassBatch];
-#pragma unroll
-                for (int u = 0; u < kPassBatch; ++u) {
-                    // window of cell i = k: triples i..i+6 = P[lane+6] - P[lane-1]
-                    const unsigned h0 = __shfl_down_sync(kFull, p0[u], 6), h1 = __shfl_down_sync(kFull, p1[u], 6);
-                    unsigned l0 = __shfl_up_sync(kFull, p0[u], 1), l1 = __shfl_up_sync(kFull, p1[u], 1);
-                    if (lane == 0) { l0 = 0; l1 = 0; }
-                    C0[u] = h0 - l0; C1[u] = h1 - l1;
-                }
-                bool dirty[kPassBatch];
-                unsigned cw[kPassBatch];
-                // the cell's 9 pixels (clamped at the crop edge: duplicates are harmless), all passes in flight
-                int px[kPassBatch][9];
-                const int y0 = kCell * cj;
-                const uint8_t* r0 = gray + min(y0, hm1) * g.gp;
-                const uint8_t* r1 = gray + min(y0 + 1, hm1) * g.gp;
-                const uint8_t* r2 = gray + min(y0 + 2, hm1) * g.gp;
-#pragma unroll
-                for (int u = 0; u < kPassBatch; ++u) {
-                    const int x0 = kCell * (kb + u * kCellsPerPass + lane);
-                    const int xa = min(x0, wm1), xb = min(x0 + 1, wm1), xc = min(x0 + 2, wm1);
-                    px[u][0] = r0[xa]; px[u][1] = r0[xb]; px[u][2] = r0[xc];
-                    px[u][3] = r1[xa]; px[u][4] = r1[xb]; px[u][5] = r1[xc];
-                    px[u][6] = r2[xa]; px[u][7] = r2[xb]; px[u][8] = r2[xc];
-                }
-#pragma unroll
-                for (int u = 0; u < kPassBatch; ++u) {
-                    const int k = kb + u * kCellsPerPass + lane;
-                    const bool cact = lane < kCellsPerPass && k < nlx;
-                    const int n263 = __popc((C0[u] + kGe263) & kFlag) + __popc((C1[u] + kGe263) & kFlag);
-                    const int n179 = __popc((C0[u] + kGe179) & kFlag) + __popc((C1[u] + kGe179) & kFlag);
-                    const int lo_idx = kLevels - n179;        // levels 0..lo_idx-1 surely have C <= 220: med >  LO
-                    const int hi_idx = kLevels - n263;        // level hi_idx surely has C >= 221:        med <= HI
-                    const int LO = lo_idx > 0 ? lv[lo_idx - 1] : -1;
-                    const int HI = hi_idx < kLevels ? lv[hi_idx] : 255;
-                    const int U1 = min(max(LO - thr + 1, 0), 255);     // defect if g <  U1
-                    const int U4 = min(HI + thr, 255);                 // defect if g >  U4
-                    const int U2 = max(HI - thr, 0);                   // clean needs g >= U2
-                    const int U3 = min(LO + thr + 1, 255);             // clean needs g <= U3
-                    cw[u] = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
-                    int mn = px[u][0], mx = px[u][0];
-#pragma unroll
-                    for (int t = 1; t < 9; ++t) { mn = min(mn, px[u][t]); mx = max(mx, px[u][t]); }
-                    dirty[u] = cact && (mn < U2 || mx > U3);
-                }
-#pragma unroll
-                for (int u = 0; u < kPassBatch; ++u) {
-                    // append the dirty cells of this pass (one atomic per warp)
-                    const unsigned dm = __ballot_sync(kFull, dirty[u]);
-                    if (dm) {
-                        const int k = kb + u * kCellsPerPass + lane;
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
-                        base = __shfl_sync(kFull, base, 0);
-                        if (dirty[u]) {
-                            const int slot = base + __popc(dm & ((1u << lane) - 1u));
-                            if (slot < w.dirty_cap) w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)k, cw[u]);
-                            else rank_dirty_cell(gray, g, thr, ROI, CAND, w, k, cj, cw[u]);
-                        }
-                    }
-                }
-            }
+            uint2* row = w.cs + jj * w.P + 1;
+            const unsigned short* cm = w.cmm + par * bufrows + jj * w.cpitch;
+            if (g.w <= 96) rank_row_cells<3>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
+            else if (g.w <= 224) rank_row_cells<7>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
+            else if (g.w <= 352) rank_row_cells<11>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
+            else rank_row_cells<15>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
         }
         __syncthreads();
         pt.acc(21);

@@ -11,14 +11,14 @@ namespace vi {
 
 // Canonical (raster-order) label of every root: 1 + number of roots with a smaller
 // run id.  Stored in acc1[root]; returns the number of components.
-__device__ inline int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
+VI_PHASE int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
     unsigned carry = 0;
     for (int base = 0; base < R; base += kThreads) {
         int i = base + threadIdx.x + 1;
-        unsigned isroot = (i <= R && ws.parent[i] == i) ? 1u : 0u;
+        unsigned isroot = (i <= R && ws.parent()[i] == i) ? 1u : 0u;
         unsigned a = isroot, b = 0, ta, tb;
         cta_excl_scan2(cs, a, b, ta, tb);
-        if (isroot) ws.acc1[i] = carry + a + 1;
+        if (isroot) ws.acc1()[i] = carry + a + 1;
         carry += ta;
     }
     __syncthreads();
@@ -26,22 +26,22 @@ __device__ inline int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
 }
 
 // int32 labels, unit-packed [h][w]: 0 background, else acc1[root].
-__device__ inline void store_labels(const Geom& g, const CclWs& ws, int32_t* __restrict__ dst) {
+VI_PHASE void store_labels(const Geom& g, const CclWs& ws, int32_t* __restrict__ dst) {
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
         int y, c; word_rc(g, i, y, c);
         int x0 = c * 32, x1 = min(x0 + 31, g.w - 1);
-        int j = ws.row_first[y], j1 = ws.row_first[y + 1];
-        while (j < j1 && (int)ws.xe[j] < x0) ++j;
+        int j = ws.row_first()[y], j1 = ws.row_first()[y + 1];
+        while (j < j1 && (int)ws.xe()[j] < x0) ++j;
         for (int x = x0; x <= x1; ++x) {
-            while (j < j1 && (int)ws.xe[j] < x) ++j;
+            while (j < j1 && (int)ws.xe()[j] < x) ++j;
             int lab = 0;
-            if (j < j1 && (int)ws.xs[j] <= x) lab = (int)ws.acc1[ws.parent[j]];
+            if (j < j1 && (int)ws.xs()[j] <= x) lab = (int)ws.acc1()[ws.parent()[j]];
             dst[(long long)y * g.w + x] = lab;
         }
     }
 }
 
-__device__ inline void zero_bytes(uint8_t* __restrict__ dst, int n) {
+VI_PHASE void zero_bytes(uint8_t* __restrict__ dst, int n) {
     const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
     for (int e = threadIdx.x; e < head; e += kThreads) dst[e] = 0;
     const int n16 = (n - head) >> 4;
@@ -51,7 +51,7 @@ __device__ inline void zero_bytes(uint8_t* __restrict__ dst, int n) {
 }
 
 // L2 prefetch of a unit's crop rows (issued for the CTA's next unit while this one computes).
-__device__ inline void prefetch_crop_l2(const KArgs& a, int uid) {
+VI_PHASE void prefetch_crop_l2(const KArgs& a, int uid) {
     const int img = uid / a.n_units, unit = uid - img * a.n_units;
     const int4 rc = a.rects[unit];
     const uint8_t* base = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
@@ -63,7 +63,7 @@ __device__ inline void prefetch_crop_l2(const KArgs& a, int uid) {
     }
 }
 
-__device__ inline void select_levels(UnitShared& sh, int npix, int thr) {
+VI_PHASE void select_levels(UnitShared& sh, int npix, int thr) {
     // Six levels around the two Otsu class medians of the (blurred) histogram.
     // Any level set is exact; these make the cell brackets decide nearly every pixel.
     if (warp_id() == 0) {
@@ -122,7 +122,7 @@ __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, 
     }
 }
 
-__device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitShared& sh) {
+__device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitShared& sh) {
     const int tid = threadIdx.x;
     const int img = uid / a.n_units, unit = uid - img * a.n_units;
     const int4 rc = a.rects[unit];
@@ -160,7 +160,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     long long* stats = a.stats_out ? a.stats_out + (long long)uid * 8 : nullptr;
 
     PhaseTimer pt;
-    pt.start(a.prof ? a.prof + (long long)uid * kProfSlots : nullptr);
+    pt.start(&sh.pt, a.prof ? a.prof + (long long)uid * kProfSlots : nullptr);
     const bool need_gray = mode == MODE_FULL || mode == MODE_SEG_ONLY || mode == MODE_DETECT;
     const bool need_seg = mode == MODE_FULL || mode == MODE_SEG_ONLY;
     int otsu_t = 0, dx = 0, dy = 0, n_runs_max = 0;
@@ -332,7 +332,7 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         int nlab = ccl_rank_roots(sh.cs, ws, R);
         if (lab_out) store_labels(g, ws, lab_out);
         if (tid == 0) {
-            stats[0] = nlab; stats[1] = broot ? (long long)ws.acc1[broot] : 0; stats[2] = area;
+            stats[0] = nlab; stats[1] = broot ? (long long)ws.acc1()[broot] : 0; stats[2] = area;
             stats[3] = (long long)sx; stats[4] = (long long)sy; stats[5] = R;
         }
         return;
@@ -377,9 +377,9 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
     // ---- P11: median residual -------------------------------------------------
     select_levels(sh, npix, thr);
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
-    if (g.w <= kThreads && rank_ws_bytes(g.w) <= plan.ws_bytes) {
+    if (g.w <= kRankMaxW && rank_ws_bytes(g.w) <= plan.ws_bytes) {
         RankWs rw = rank_ws_carve(WS, g.w, MA, MB, plan.mask_bytes);
-        rank_tables(sh.levels, rw);
+        rank_tables(sh.levels, thr, rw);
         __syncthreads();
         pt.tick();   // 10 levels + tables
         n_amb = rank_stage_lattice(sh.cs, gray, g, rw, sh.levels, thr, MD, MC, pt);
@@ -430,23 +430,23 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
         for (int base = 0; base < Rpad; base += kThreads) {
             int i = base + tid + 1;
             bool valid = i <= R;
-            int root = valid ? ws.parent[i] : 0;
-            unsigned a2 = valid ? run_quad_area2(MB, g, ws.yy[i], ws.xs[i], ws.xe[i]) : 0u;
-            agg_add(ws.acc0, valid, root, a2);
+            int root = valid ? ws.parent()[i] : 0;
+            unsigned a2 = valid ? run_quad_area2(MB, g, ws.yy()[i], ws.xs()[i], ws.xe()[i]) : 0u;
+            agg_add(ws.acc0(), valid, root, a2);
         }
     }
     __syncthreads();
     const long long min_area = a.p.min_area;
     long long max_area = (long long)__double2ll_rz(__dmul_rn((double)roi_area, a.p.max_area_frac));
     if (max_area < min_area) max_area = min_area;
-    const unsigned* acc0 = ws.acc0;
+    const unsigned* acc0 = ws.acc0();
     auto keep = [acc0, min_area, max_area](int root) {
         long long a2 = acc0[root];
         return a2 >= 2 * min_area && a2 <= 2 * max_area;
     };
     unsigned long long kept = 0;
     for (int i = 1 + tid; i <= R; i += kThreads)
-        if (ws.parent[i] == i && keep(i)) ++kept;
+        if (ws.parent()[i] == i && keep(i)) ++kept;
     const int n_kept = (int)cta_sum_u64(sh.cs, kept);
     ccl_paint(ME, nullptr, g, ws, keep);
     __syncthreads();
@@ -461,8 +461,16 @@ __device__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitS
 }
 
 __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ UnitShared sh;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ UnitShared sh_raw;
+    // The two shared-memory bases are made opaque once: ptxas otherwise re-derives them (S2UR SR_CgaCtaId + a chain
+    // of uniform ops) next to nearly every access instead of holding them, also inside the serial Otsu recurrence.
+    unsigned char* smem = smem_raw;
+    UnitShared* shp = &sh_raw;
+    asm volatile("" : "+l"(smem), "+l"(shp));
+    __builtin_assume(__isShared(smem));
+    __builtin_assume(__isShared(shp));
+    UnitShared& sh = *shp;
     const int n_total = a.n_images * a.n_units;
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
         process_unit(a, uid, smem, sh);
