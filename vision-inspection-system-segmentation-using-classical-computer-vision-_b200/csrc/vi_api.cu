@@ -71,6 +71,7 @@ struct vi_ctx {
     DevBuf scratch;
     long long scratch_stride = 0;
     long long scratch_f32_off = 0;
+    long long scratch_rank_off = 0;
     // compat / host-batch staging
     DevBuf st_in, st_aux, st_out, st_out2, st_rec, st_stats, st_lab;
     DevBuf hb_frames[2], hb_seg[2], hb_def[2], hb_rec[2];
@@ -375,6 +376,8 @@ static int ensure_scratch(vi_ctx* c, int wmax, int hmax, int nblocks, bool f32_p
     long long px4 = (long long)((wmax + 3) & ~3) * hmax;
     long long stride = ((px * 2 + 15) & ~15ll) + ((px4 + 15) & ~15ll) + (long long)ccl_ws_bytes((int)capg, hmax) + 256;
     stride = (stride + 255) & ~255ll;
+    c->scratch_rank_off = stride;
+    stride += (rank_scratch_bytes(wmax, hmax) + 255) & ~255ll;
     c->scratch_f32_off = stride;
     if (f32_plane) stride += (px * 4 + 255) & ~255ll;       // float plane of the adaptive mean, only when asked for
     c->scratch_stride = stride;
@@ -393,6 +396,7 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     a.scratch = (uint8_t*)c->scratch.p + (size_t)slot * c->sm_count * c->scratch_stride;
     a.scratch_stride = c->scratch_stride;
     a.scratch_f32_off = c->scratch_f32_off;
+    a.scratch_rank_off = c->scratch_rank_off;
     a.wmax = gs.wmax; a.hmax = gs.hmax;
     a.plan = gs.plan;
     a.prof = (&gs == &c->grid) ? c->prof : nullptr;

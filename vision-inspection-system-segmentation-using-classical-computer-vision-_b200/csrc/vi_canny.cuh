@@ -73,10 +73,10 @@ VI_PHASE int canny_hysteresis(CtaScratch& cs, const unsigned* CAND, const unsign
             hit |= STRONG[y * g.wpr + c] & bit_range(max(xs, c * 32) - c * 32, min(xe, c * 32 + 31) - c * 32);
         if (hit) ws.acc0()[ws.parent()[i]] = 1u;          // every writer stores the same value
     }
-    __syncthreads();
+    cta_sync();
     const unsigned* acc0 = ws.acc0();
     ccl_paint(EDGES, nullptr, g, ws, [acc0](int root) { return acc0[root] != 0u; });
-    __syncthreads();
+    cta_sync();
     return R;
 }
 

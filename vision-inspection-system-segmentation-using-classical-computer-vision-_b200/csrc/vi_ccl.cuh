@@ -74,7 +74,7 @@ __device__ inline void ccl_jump(int* parent, int R) {
             q = parent[q];
             if (q != p) { parent[i] = q; changed = 1; }
         }
-        if (!__syncthreads_or(changed)) break;
+        if (!cta_sync_or(changed)) break;
     }
 }
 
@@ -124,7 +124,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
         }
     }
     if (threadIdx.x == 0) { ws.row_first()[g.h] = (int)R + 1; ws.parent()[0] = 0; ws.acc0()[0] = 0; ws.acc1()[0] = 0; }
-    __syncthreads();
+    cta_sync();
     if (pt) pt->acc(24);
     const int c8 = conn8 ? 1 : 0;
     // A: primary link = first overlapping run of the row above
@@ -145,7 +145,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
         ws.acc0()[i] = 0;
         ws.acc1()[i] = 0;
     }
-    __syncthreads();
+    cta_sync();
     if (pt) pt->acc(25);
     ccl_jump(ws.parent(), (int)R);
     if (pt) pt->acc(26);
@@ -164,7 +164,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
         }
         if (border && (y == 0 || y == g.h - 1 || xs == 0 || xe == g.w - 1)) uf_unite(ws.parent(), i, 0);
     }
-    __syncthreads();
+    cta_sync();
     if (pt) pt->acc(27);
     ccl_jump(ws.parent(), (int)R);
     if (pt) pt->acc(28);
@@ -238,7 +238,7 @@ VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
         unsigned len = valid ? (unsigned)(ws.xe()[i] - ws.xs()[i] + 1) : 0u;
         agg_add(ws.acc0(), valid, root, len);
     }
-    __syncthreads();
+    cta_sync();
     unsigned long long best = 0;
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
         if (ws.parent()[i] == i) {
@@ -249,7 +249,7 @@ VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
     // min block key among the components of maximal area
     const int w2 = (g.w + 1) / 2;
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads) ws.acc1()[i] = 0xffffffffu;
-    __syncthreads();
+    cta_sync();
     for (int base = 0; base < Rpad; base += kThreads) {
         int i = base + threadIdx.x + 1;
         bool valid = i <= R;
@@ -258,7 +258,7 @@ VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
         unsigned key = valid ? (unsigned)((ws.yy()[i] >> 1) * w2 + (ws.xs()[i] >> 1)) : 0xffffffffu;
         agg_min(ws.acc1(), valid, root, key);
     }
-    __syncthreads();
+    cta_sync();
     unsigned long long sel = 0;   // pick (min key) -> encode as max of (~key, root)
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads)
         if (ws.parent()[i] == i && ws.acc0()[i] == amax) {

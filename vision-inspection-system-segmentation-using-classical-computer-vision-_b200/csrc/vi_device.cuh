@@ -16,8 +16,9 @@ namespace vi {
 // arguments then live in local memory and the labelling phases ran 2-3x slower.)
 #define VI_PHASE __device__ inline
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 512;       // worker threads: every phase loop strides by this
 constexpr int kWarps = kThreads / 32;
+constexpr int kOtsuWarp = kWarps - 1;   // this warp advances the exact Otsu recurrence while others walk columns (vi_rank.cuh)
 constexpr int kHistWords = 2048;   // per-warp lane-private histogram: [64 bin-quads][32 lanes] u32, 4 x 8-bit counters
 constexpr int kHistBytes = kHistWords * 4;
 constexpr int kMaxExcl = 32;
@@ -90,8 +91,9 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
     int cpitch = ((wmax + 2) / 3 + 2) & ~1;
     int rch = wmax <= 96 ? 3 : wmax <= 224 ? 7 : wmax <= 352 ? 11 : 15;
-    int band = wmax <= 480 ? 16 * (32 * rch + 2) * 8 + 32 * cpitch * 2 + 64 * 4 + 64 : 0;   // vi_rank.cuh: rank_ws_bytes
-    int otsu = 256 * 8 * 6 + 256;
+    int band = wmax <= 480 ? 16 * (32 * rch + 2) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
+    int otsu = 3 * 256 * 8 + 64;                // vi_pipeline.cuh: kOtsuWsBytes, at the end of the workspace
+    band += otsu;                               // the Otsu warp works next to the rank-count cell pass
     int rowfirst = align16((hmax + 2) * 4);
     int want_cap = 2048;
     int ccl = rowfirst + (want_cap + 1) * 18 + 64;
@@ -148,6 +150,7 @@ struct KArgs {
     uint8_t* scratch;               // per-CTA global scratch (general blur path, run-table overflow)
     long long scratch_stride;
     long long scratch_f32_off;      // offset of the float plane inside a CTA's scratch (adaptive threshold only)
+    long long scratch_rank_off;     // offset of the rank-count lists (dirty cells, ambiguous pixels)
     int wmax, hmax;
     long long* prof;                // diagnostics: [n_total][32] per-phase cycle counts, or null
     SmemPlan plan;
@@ -190,6 +193,9 @@ struct PhaseTimer {
 };
 
 
+__device__ __forceinline__ void cta_sync() { __syncthreads(); }
+__device__ __forceinline__ int cta_sync_or(int pred) { return __syncthreads_or(pred); }
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
@@ -204,7 +210,7 @@ __device__ inline void cta_excl_scan2(CtaScratch& cs, unsigned& a, unsigned& b, 
         if (lane >= o) { ia += xa; ib += xb; }
     }
     if (lane == 31) { cs.wa[warp] = ia; cs.wb[warp] = ib; }
-    __syncthreads();
+    cta_sync();
     if (warp == 0) {
         unsigned va = lane < kWarps ? cs.wa[lane] : 0u;
         unsigned vb = lane < kWarps ? cs.wb[lane] : 0u;
@@ -218,12 +224,12 @@ __device__ inline void cta_excl_scan2(CtaScratch& cs, unsigned& a, unsigned& b, 
         if (lane < kWarps) { cs.wa[lane] = sa - va; cs.wb[lane] = sb - vb; }
         if (lane == kWarps - 1) { cs.tot_a = sa; cs.tot_b = sb; }
     }
-    __syncthreads();
+    cta_sync();
     a = ia - a + cs.wa[warp];
     b = ib - b + cs.wb[warp];
     ta = cs.tot_a;
     tb = cs.tot_b;
-    __syncthreads();
+    cta_sync();
 }
 
 __device__ inline unsigned long long cta_sum_u64(CtaScratch& cs, unsigned long long v) {
@@ -231,16 +237,16 @@ __device__ inline unsigned long long cta_sum_u64(CtaScratch& cs, unsigned long l
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
     if (lane == 0) cs.wl[warp] = v;
-    __syncthreads();
+    cta_sync();
     if (warp == 0) {
         unsigned long long t = lane < kWarps ? cs.wl[lane] : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(kFull, t, o);
         if (lane == 0) cs.tot_l = t;
     }
-    __syncthreads();
+    cta_sync();
     unsigned long long r = cs.tot_l;
-    __syncthreads();
+    cta_sync();
     return r;
 }
 
@@ -252,7 +258,7 @@ __device__ inline unsigned long long cta_max_u64(CtaScratch& cs, unsigned long l
         v = x > v ? x : v;
     }
     if (lane == 0) cs.wl[warp] = v;
-    __syncthreads();
+    cta_sync();
     if (warp == 0) {
         unsigned long long t = lane < kWarps ? cs.wl[lane] : 0ull;
 #pragma unroll
@@ -262,9 +268,9 @@ __device__ inline unsigned long long cta_max_u64(CtaScratch& cs, unsigned long l
         }
         if (lane == 0) cs.tot_l = t;
     }
-    __syncthreads();
+    cta_sync();
     unsigned long long r = cs.tot_l;
-    __syncthreads();
+    cta_sync();
     return r;
 }
 
@@ -386,7 +392,7 @@ VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsign
             for (int d = 1; d <= r; ++d) v &= __funnelshift_r(C, R, d) & __funnelshift_l(L, C, d);
             nxt[i] = v & row_mask_of(g, c);
         }
-        __syncthreads();
+        cta_sync();
         cur = nxt;
         nxt = (cur == bufA) ? bufB : bufA;
         // vertical: AND of the 2r+1 rows (edge row replicated)
@@ -396,7 +402,7 @@ VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsign
             for (int d = 1; d <= r; ++d) v &= cur[max(y - d, 0) * g.wpr + c] & cur[min(y + d, g.h - 1) * g.wpr + c];
             nxt[i] = v;
         }
-        __syncthreads();
+        cta_sync();
         return nxt;
     }
     int a = 0;
@@ -408,7 +414,7 @@ VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsign
             if (a == 0) v &= cur[i];
             nxt[i] = v & row_mask_of(g, c);
         }
-        __syncthreads();
+        cta_sync();
         a += b;
         cur = nxt;
         nxt = (cur == bufA) ? bufB : bufA;
@@ -422,7 +428,7 @@ VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsign
             if (a == 0) v &= cur[i];
             nxt[i] = v;
         }
-        __syncthreads();
+        cta_sync();
         a += b;
         cur = nxt;
         nxt = (cur == bufA) ? bufB : bufA;

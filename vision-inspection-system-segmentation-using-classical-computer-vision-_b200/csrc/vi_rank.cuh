@@ -36,7 +36,7 @@
 //       two field-parallel compares give the bracket, a 49-entry table the four
 //       byte thresholds, and the cell min / max decide clean or dirty.
 #pragma once
-#include "vi_device.cuh"
+#include "vi_pipeline.cuh"
 
 namespace vi {
 
@@ -54,10 +54,10 @@ struct RankWs {
     uint2* cs;          // [kLatBand][P] (0, then per column) 7-block column sums, then their prefix over x
     unsigned short* cmm;// [2][kLatBand][cpitch] cell gray min | (255 - max) << 8
     unsigned* table;    // [49] thresholds U1 | U2 << 8 | U3 << 16 | U4 << 24 by (n179, n263)
-    uint2* dirty;       // [dirty_cap] (cell position, thresholds); more are classified inline
-    unsigned* exact;    // [exact_cap] ambiguous pixels (y << 16 | x); more are counted inline
-    int dirty_cap, exact_cap;
-    int* counters;      // [0] dirty cells, [1] ambiguous pixels listed, [2] ambiguous pixels total
+    uint2* dirty;       // [cells] (cell position, thresholds), in the CTA's global scratch: every cell fits
+    unsigned* exact;    // [exact_cap] ambiguous pixels (y << 16 | x), global scratch; more are counted inline
+    int exact_cap;
+    int* counters;      // shared: [0] dirty cells, [1] ambiguous pixels listed, [2] ambiguous pixels total
     int P, cpitch;
 };
 
@@ -69,21 +69,32 @@ __host__ __device__ inline int rank_ch(int w) { return w <= 96 ? 3 : w <= 224 ? 
 __host__ __device__ inline int rank_P(int w) { return 32 * rank_ch(w) + 2; }
 __host__ __device__ inline int rank_cpitch(int w) { return ((w + kCell - 1) / kCell + 2) & ~1; }      // cells + a dummy slot
 __host__ __device__ inline int rank_ws_bytes(int w) {
-    return kLatBand * rank_P(w) * 8 + kCmmRows * rank_cpitch(w) * 2 + 64 * 4 + 64;
+    return kLatBand * rank_P(w) * 8 + kCmmRows * rank_cpitch(w) * 2 + 64 * 4;
 }
 
-// The two lists live in two mask buffers that are idle during this stage.
-__device__ inline RankWs rank_ws_carve(unsigned char* base, int w, unsigned* listA, unsigned* listB, int mask_bytes) {
+constexpr int kExactCap = 4096;
+__host__ __device__ inline long long rank_scratch_bytes(int wmax, int hmax) {
+    return (long long)((wmax + kCell - 1) / kCell) * ((hmax + kCell - 1) / kCell) * 8 + kExactCap * 4;
+}
+
+// The cell pass runs before the ROI exists (next to the Otsu scan), the per-pixel pass after it: the two lists
+// outlive the shared workspace, so they sit in the CTA's global scratch (L2-resident) and the counters in static
+// shared memory.
+__device__ inline RankWs rank_ws_carve(unsigned char* base, int w, unsigned char* lists, int wmax, int hmax, int* counters) {
     RankWs r;
     r.P = rank_P(w); r.cpitch = rank_cpitch(w);
     r.cs = reinterpret_cast<uint2*>(base); base += kLatBand * r.P * 8;
     r.cmm = reinterpret_cast<unsigned short*>(base); base += kCmmRows * r.cpitch * 2;
-    r.table = reinterpret_cast<unsigned*>(base); base += 64 * 4;
-    r.counters = reinterpret_cast<int*>(base);
-    r.dirty = reinterpret_cast<uint2*>(listA); r.dirty_cap = mask_bytes / 8;
-    r.exact = listB; r.exact_cap = mask_bytes / 4;
+    r.table = reinterpret_cast<unsigned*>(base);
+    r.counters = counters;
+    r.dirty = reinterpret_cast<uint2*>(lists);
+    r.exact = reinterpret_cast<unsigned*>(lists + (long long)((wmax + kCell - 1) / kCell) * ((hmax + kCell - 1) / kCell) * 8);
+    r.exact_cap = kExactCap;
     return r;
 }
+
+__device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int thr, const unsigned* ROI, unsigned* CAND,
+                                       RankWs& w, int ci, int cj, unsigned cw);
 
 VI_PHASE void rank_tables(const int* lv, int thr, RankWs w) {
     const int v = threadIdx.x;
@@ -151,9 +162,7 @@ __device__ __forceinline__ unsigned mm_pack(unsigned q) { return q * 0xFFFF0001u
 
 // S + C for one lattice row (one warp).  CH = columns per lane of the prefix pass (odd).
 template <int CH>
-__device__ __forceinline__ void rank_row_cells(const uint8_t* gray, const Geom& g, RankWs& w, uint2* row,
-                                               const unsigned short* cm, int cj, int nlx, int thr, const unsigned* ROI,
-                                               unsigned* CAND) {
+__device__ __forceinline__ void rank_row_cells(const Geom& g, RankWs& w, uint2* row, const unsigned short* cm, int cj, int nlx) {
     const int lane = lane_id();
     const int wm1 = g.w - 1;
     {   // ---- S: inclusive prefix over the row ---------------------------------------
@@ -202,8 +211,7 @@ __device__ __forceinline__ void rank_row_cells(const uint8_t* gray, const Geom& 
             base = __shfl_sync(kFull, base, 0);
             if (dirty) {
                 const int slot = base + __popc(dm & ((1u << lane) - 1u));
-                if (slot < w.dirty_cap) w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)i, cw);
-                else rank_dirty_cell(gray, g, thr, ROI, CAND, w, i, cj, cw);
+                w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)i, cw);
             }
         }
     }
@@ -277,13 +285,15 @@ __device__ __forceinline__ void v_band(VState& st, unsigned T0, unsigned T1, con
     }
 }
 
-// CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
-// Returns the number of pixels that needed an exact rank count.
-VI_PHASE int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom& g, RankWs w, const int* lv,
-                                         int thr, const unsigned* ROI, unsigned* CAND, PhaseTimer& pt) {
-    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+// Part 1 (needs only the gray crop and the levels): window counts on the lattice, list of dirty cells.
+// The warp kOtsuWarp carries the exact Otsu scan along when it owns no column: q1 sums and reciprocals during the
+// first band, a slice of the mu1 recurrence during each further band, the rest at the end; *otsu_t holds the
+// threshold on return.
+VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, const unsigned* hist, int npix,
+                         double* ows, int olast, int* otsu_t, PhaseTimer& pt) {
+    const int lane = lane_id(), warp = warp_id();
     const int nly = (g.h + kCell - 1) / kCell, nlx = (g.w + kCell - 1) / kCell;
-    const int hm1 = g.h - 1, wm1 = g.w - 1;
+    const int hm1 = g.h - 1;
     // V: the first 3*cpw lanes of warp v own columns 3*cpw*v .. (cpw whole cells); columns past the
     // crop edge re-read the edge column (duplicates never change a cell's min / max)
     const int cpw = kColsPerWarp / kCell;                    // cells per warp: full warps (the pass is issue / smem-pipe bound)
@@ -319,9 +329,18 @@ VI_PHASE int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom
     asm volatile("" : "+r"(P), "+r"(cpitch), "+r"(gp));
     const int csx = vact ? 1 + vcol : P - 1;                  // column slot (dummy for lanes without a column)
     const int cmx = cell_lead ? vcell : cpitch - 1;           // cell slot (dummy for lanes that lead no cell)
+    OtsuJob job;
+    const bool owarp = warp == kOtsuWarp;
+    const bool oslice = owarp && !vwarp;                      // idle during V: the scan rides along
+    const int nbands = (nly + kLatBand - 1) / kLatBand;
+    int per = 256;
     int par = 0;
     for (int j0 = 0; j0 < nly; j0 += kLatBand, par ^= 1) {
         const int j1 = min(j0 + kLatBand, nly);
+        if (oslice) {
+            if (j0 == 0) { otsu_begin(job, hist, npix, ows, olast); per = nbands > 1 ? (job.imax - job.imin + nbands - 1) / (nbands - 1) : 256; }
+            else otsu_chain(job, per);
+        }
         // ---- V: blocks j0+3 .. j0+18 of every column -----------------------------------
         if (vwarp) {
             unsigned short* cmA = w.cmm + par * bufrows + cmx;
@@ -331,27 +350,41 @@ VI_PHASE int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom
             else
                 v_band<true>(st, T0, T1, gcol, gp, hm1, j0, w.cs + csx, P, cmA, cmB, cpitch);
         }
-        __syncthreads();
+        cta_sync();
         pt.acc(20);
         // ---- S + C: one warp per lattice row ------------------------------------------
         for (int jj = warp; jj < j1 - j0; jj += kWarps) {
             uint2* row = w.cs + jj * w.P + 1;
             const unsigned short* cm = w.cmm + par * bufrows + jj * w.cpitch;
-            if (g.w <= 96) rank_row_cells<3>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
-            else if (g.w <= 224) rank_row_cells<7>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
-            else if (g.w <= 352) rank_row_cells<11>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
-            else rank_row_cells<15>(gray, g, w, row, cm, j0 + jj, nlx, thr, ROI, CAND);
+            if (g.w <= 96) rank_row_cells<3>(g, w, row, cm, j0 + jj, nlx);
+            else if (g.w <= 224) rank_row_cells<7>(g, w, row, cm, j0 + jj, nlx);
+            else if (g.w <= 352) rank_row_cells<11>(g, w, row, cm, j0 + jj, nlx);
+            else rank_row_cells<15>(g, w, row, cm, j0 + jj, nlx);
         }
-        __syncthreads();
+        cta_sync();
         pt.acc(21);
     }
+    if (owarp) {
+        if (!oslice) otsu_begin(job, hist, npix, ows, olast);
+        const int t = otsu_end(job);
+        if (lane == 0) *otsu_t = t;
+    }
+    cta_sync();
+}
+
+// Part 2 (needs the ROI): CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
+// Returns the number of pixels that needed an exact rank count.
+VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, int thr, const unsigned* ROI, unsigned* CAND,
+                         PhaseTimer& pt) {
+    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const int hm1 = g.h - 1, wm1 = g.w - 1;
     // ---- dirty cells: per-pixel classification ----------------------------------------
-    const int nd = min(w.counters[0], w.dirty_cap);
+    const int nd = w.counters[0];
     for (int i = tid; i < nd; i += kThreads) {
         const uint2 e = w.dirty[i];
         rank_dirty_cell(gray, g, thr, ROI, CAND, w, (int)(e.x & 0xffffu), (int)(e.x >> 16), e.y);
     }
-    __syncthreads();
+    cta_sync();
     pt.acc(22);
     // ---- ambiguous pixels: exact rank counts, one warp per pixel -------------------------
     const int ne = min(w.counters[1], w.exact_cap);
@@ -375,10 +408,9 @@ VI_PHASE int rank_stage_lattice(CtaScratch& cs_, const uint8_t* gray, const Geom
         cb = __reduce_add_sync(kFull, cb);
         if (lane == 0 && (ca <= 220 || cb >= 221)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
     }
-    __syncthreads();
+    cta_sync();
     const int total = w.counters[2];
-    __syncthreads();
-    (void)cs_;
+    cta_sync();
     return total;
 }
 

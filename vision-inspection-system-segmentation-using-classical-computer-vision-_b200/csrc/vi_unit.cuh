@@ -21,7 +21,7 @@ VI_PHASE int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
         if (isroot) ws.acc1()[i] = carry + a + 1;
         carry += ta;
     }
-    __syncthreads();
+    cta_sync();
     return (int)carry;
 }
 
@@ -63,12 +63,11 @@ VI_PHASE void prefetch_crop_l2(const KArgs& a, int uid) {
     }
 }
 
-VI_PHASE void select_levels(UnitShared& sh, int npix, int thr) {
+VI_PHASE void select_levels(UnitShared& sh, int npix, int thr, int t) {
     // Six levels around the two Otsu class medians of the (blurred) histogram.
     // Any level set is exact; these make the cell brackets decide nearly every pixel.
     if (warp_id() == 0) {
         const int lane = lane_id();
-        const int t = sh.otsu_t;
         unsigned c[8], tot = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { tot += sh.hist[lane * 8 + k]; c[k] = tot; }      // inclusive within the lane
@@ -107,7 +106,7 @@ VI_PHASE void select_levels(UnitShared& sh, int npix, int thr) {
             sh.levels[3] = min(254, max(0, l3)); sh.levels[4] = min(254, max(0, l4)); sh.levels[5] = min(254, max(0, l5));
         }
     }
-    __syncthreads();
+    cta_sync();
 }
 
 __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, int otsu_t, unsigned seg_area,
@@ -148,6 +147,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     uint8_t* g_blur = gs + ((maxpx * 2 + 15) & ~15ll);
     unsigned char* g_ccl = g_blur + ((maxpx4 + 15) & ~15ll);
     const int capg = a.hmax * (a.wmax / 2 + 1);
+    unsigned char* g_rank = gs + a.scratch_rank_off;
     const CclWs ws_s = ccl_ws_carve(WS, plan.run_cap, a.hmax);
     const CclWs ws_g = ccl_ws_carve(g_ccl, capg, a.hmax);
     CclWs ws;
@@ -174,7 +174,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         else
             load_gray(src, a.row_pitch, g, gray);
         if (uid + (int)gridDim.x < a.n_images * a.n_units) prefetch_crop_l2(a, uid + (int)gridDim.x);
-        __syncthreads();
+        cta_sync();
         pt.tick();   // 0 gather
         // ---- P1: blur + histogram ------------------------------------------------
         int src_mode = (mode == MODE_DETECT || a.blur_k == 0) ? 0 : (a.blur_k == 3 ? 1 : 2);
@@ -183,7 +183,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             // the adaptive mean reads the blurred crop from global scratch whatever the blur size
             if (a.blur_k == 0) {
                 for (int e = tid; e < npix; e += kThreads) { const int y = e / g.w; g_blur[e] = gray[y * g.gp + (e - y * g.w)]; }
-                __syncthreads();
+                cta_sync();
             } else {
                 blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
             }
@@ -194,35 +194,56 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         unsigned* hist_base = reinterpret_cast<unsigned*>(Rg);
         for (int i = tid; i < plan.n_hist * kHistWords; i += kThreads) hist_base[i] = 0;
         if (tid < 256) sh.hist[tid] = 0;
-        __syncthreads();
+        cta_sync();
         if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
             // default path: one histogram round on min(16, n_hist) warps
             blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0);
-            __syncthreads();
+            cta_sync();
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
-            __syncthreads();
+            cta_sync();
         } else {
             for (int r0 = 0; r0 < kWarps; r0 += plan.n_hist) {
                 unsigned* hw = hist_base + (warp_id() - r0) * kHistWords;
                 if (src_mode == 0) blur_pass<0, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
                 else if (src_mode == 1) blur_pass<1, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
                 else blur_pass<2, true>(gray, g_blur, g, hw, sh.hist, r0, plan.n_hist, nullptr, 0);
-                __syncthreads();
+                cta_sync();
                 hist_collect(hist_base, min(plan.n_hist, kWarps - r0), sh.hist, true);
-                __syncthreads();
+                cta_sync();
             }
         }
         pt.tick();   // 1 blur + histogram
-        // ---- P2: Otsu ------------------------------------------------------------
-        OtsuWs ow;
-        ow.p = reinterpret_cast<double*>(WS);
-        ow.ip = ow.p + 256; ow.q1 = ow.ip + 256; ow.r = ow.q1 + 256; ow.mu1 = ow.r + 256;
-        ow.key = reinterpret_cast<unsigned long long*>(ow.mu1 + 256);
-        ow.nz = reinterpret_cast<unsigned*>(ow.key + 256);
-        otsu_t = otsu_scan(sh.cs, sh.hist, npix, ow);
-        if (tid == 0) sh.otsu_t = otsu_t;
-        __syncthreads();
-        pt.tick();   // 2 otsu
+        // ---- P2: Otsu.  The exact scan is a serial recurrence in doubles: one warp advances it in slices while
+        // the others walk the columns of the median stage's cell pass, which needs no mask and only approximate
+        // levels (an approximate threshold splits the histogram into its classes).
+        double* ows = reinterpret_cast<double*>(WS + plan.ws_bytes - kOtsuWsBytes);
+        const bool lattice = (mode == MODE_FULL || mode == MODE_DETECT) && a.p.defect_method == 0 && g.w <= kRankMaxW &&
+                             rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes;
+        if (warp_id() == 0) {
+            int last;
+            const int ta = otsu_approx_warp(sh.hist, npix, last);
+            if (lane_id() == 0) { sh.t_apx = ta; sh.otsu_last = last; }
+        }
+        cta_sync();
+        if (lattice) {
+            select_levels(sh, npix, a.p.threshold, sh.t_apx);
+            RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
+            rank_tables(sh.levels, a.p.threshold, rw);
+            cta_sync();
+            pt.tick();   // 2 approximate threshold, levels, tables
+            rank_cells(gray, g, rw, sh.levels, sh.hist, npix, ows, sh.otsu_last, &sh.otsu_t, pt);
+        } else {
+            if (warp_id() == kOtsuWarp) {
+                OtsuJob job;
+                otsu_begin(job, sh.hist, npix, ows, sh.otsu_last);
+                const int t = otsu_end(job);
+                if (lane_id() == 0) sh.otsu_t = t;
+            }
+            cta_sync();
+            pt.tick();
+        }
+        otsu_t = sh.otsu_t;
+        pt.tick();   // 3 cell pass with the exact Otsu scan inside
 
         if (need_seg) {
             // ---- P3: inverse threshold ------------------------------------------
@@ -231,34 +252,34 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             else if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             else if (src_mode == 1) {
                 threshold_gray(gray, g, MB, otsu_t);
-                __syncthreads();
+                cta_sync();
                 pt.acc(29);
                 threshold_band(gray, g, MB, MA, MC, otsu_t);
             }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
-            __syncthreads();
-            pt.tick();   // 3 threshold
+            cta_sync();
+            pt.tick();   // 4 threshold
             // ---- P4: close, open --------------------------------------------------
             if (a.se_k == 3) {
-                cross3_pass<false>(MA, MB, g); __syncthreads();
-                cross3_pass<true>(MB, MA, g); __syncthreads();
-                cross3_pass<true>(MA, MB, g); __syncthreads();
-                cross3_pass<false>(MB, MA, g); __syncthreads();
+                cross3_pass<false>(MA, MB, g); cta_sync();
+                cross3_pass<true>(MB, MA, g); cta_sync();
+                cross3_pass<true>(MA, MB, g); cta_sync();
+                cross3_pass<false>(MB, MA, g); cta_sync();
             } else if (a.se_k > 0) {
-                se_pass<false>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
-                se_pass<true>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
-                se_pass<true>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
-                se_pass<false>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); __syncthreads();
+                se_pass<false>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
+                se_pass<true>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
+                se_pass<true>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
+                se_pass<false>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
             }
-            pt.tick();   // 4 close/open
+            pt.tick();   // 5 close/open
             // ---- P5: hole fill ----------------------------------------------------
             for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
-            __syncthreads();
+            cta_sync();
             int R = ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
             n_runs_max = max(n_runs_max, R);
             ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
-            __syncthreads();
-            pt.tick();   // 5 hole fill
+            cta_sync();
+            pt.tick();   // 6 hole fill
             if (mode == MODE_FULL) {
                 // ---- P6: largest 8-component centroid, shift ---------------------
                 R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws, &pt);
@@ -276,15 +297,15 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
                         }
                     }
                 }
-                __syncthreads();
-                pt.tick();   // 6 centroid labelling
+                cta_sync();
+                pt.tick();   // 7 centroid labelling
                 // ---- P7: exclusions ------------------------------------------------
-                if (a.n_excl > 0) { apply_exclusions(MA, g, a.excl, a.n_excl, dx, dy); __syncthreads(); }
+                if (a.n_excl > 0) { apply_exclusions(MA, g, a.excl, a.n_excl, dx, dy); cta_sync(); }
             }
             // ---- P8: seg mask out -------------------------------------------------
             seg_area = cta_popcount(sh.cs, MA, g);
             if (seg_out) store_mask_bytes(MA, g, seg_out);
-            pt.tick();   // 7 exclusions + seg mask out
+            pt.tick();   // 8 exclusions + seg mask out
             if (mode == MODE_SEG_ONLY) {
                 write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, 0, 0, 0, cx, cy, 0, n_runs_max);
                 return;
@@ -294,14 +315,14 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
 
     if (mode == MODE_FILL || mode == MODE_STATS || mode == MODE_ERODE || mode == MODE_LABEL || mode == MODE_DETECT) {
         load_mask_bits(aux, g, MA);
-        __syncthreads();
+        cta_sync();
     }
     if (mode == MODE_FILL) {
         for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
-        __syncthreads();
+        cta_sync();
         ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
         ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
-        __syncthreads();
+        cta_sync();
         store_mask_bytes(MA, g, seg_out);
         return;
     }
@@ -343,7 +364,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     // ---- P9: square erosion ---------------------------------------------------
     unsigned* X = MA;
     if (a.p.erode_px > 0) X = erode_square_bits(MA, MB, MC, g, a.p.erode_px);
-    pt.tick();   // 8 erosion
+    pt.tick();   // 9 erosion
     // ---- P10: largest 8-component = ROI ---------------------------------------
     int R = ccl_build(sh.cs, X, g, true, false, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
@@ -359,34 +380,29 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         return;
     }
     ccl_paint(MD, nullptr, g, ws, [broot](int root) { return root == broot; });
-    __syncthreads();
-    pt.tick();   // 9 ROI labelling
+    cta_sync();
+    pt.tick();   // 10 ROI labelling
     const int thr = a.p.threshold;
     int n_amb = 0;
     int any_resid = 0;
     if (a.p.defect_method == 1) {
         // ---- P11': Canny edges inside the ROI (indexing_ui.py:1536-1539) ----------------
         canny_candidates(gray, g, a.canny_low, a.canny_high, MA, MB);
-        __syncthreads();
+        cta_sync();
         R = canny_hysteresis(sh.cs, MA, MB, MC, g, ws_s, ws_g, ws);
         n_runs_max = max(n_runs_max, R);
         for (int i = tid; i < g.nwords; i += kThreads) { const unsigned v = MC[i] & MD[i]; MB[i] = v; any_resid |= (v != 0); }
-        any_resid = __syncthreads_or(any_resid);
-        for (int k = 0; k < 4; ++k) pt.tick();   // 10..13 (the residual path's slots)
+        any_resid = cta_sync_or(any_resid);
+        for (int k = 0; k < 2; ++k) pt.tick();   // 11, 12 (the residual path's slots)
     } else {
-    // ---- P11: median residual -------------------------------------------------
-    select_levels(sh, npix, thr);
+    // ---- P11: median residual (second part: the dirty cells against the ROI) ------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
-    if (g.w <= kRankMaxW && rank_ws_bytes(g.w) <= plan.ws_bytes) {
-        RankWs rw = rank_ws_carve(WS, g.w, MA, MB, plan.mask_bytes);
-        rank_tables(sh.levels, thr, rw);
-        __syncthreads();
-        pt.tick();   // 10 levels + tables
-        n_amb = rank_stage_lattice(sh.cs, gray, g, rw, sh.levels, thr, MD, MC, pt);
-        pt.tick();   // 11 rank stage remainder
+    cta_sync();
+    if (g.w <= kRankMaxW && rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes) {
+        RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
+        n_amb = rank_finish(gray, g, rw, thr, MD, MC, pt);
     } else {
         // units wider than the column-per-thread pass: exact rank count for every ROI pixel
-        __syncthreads();
         for (int i = tid; i < g.nwords; i += kThreads) {
             unsigned q = MD[i], add = 0;
             int y, c; word_rc(g, i, y, c);
@@ -396,18 +412,16 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             }
             MC[i] = add;
         }
-        __syncthreads();
+        cta_sync();
         n_amb = (int)roi_area;
-        pt.tick();
-        pt.tick();
     }
-    pt.tick();   // 12 (unused)
+    pt.tick();   // 11 dirty cells + exact counts
     // ---- P12: open with the 3x3 cross -----------------------------------------
-    cross3_pass<true>(MC, MA, g); __syncthreads();
+    cross3_pass<true>(MC, MA, g); cta_sync();
     cross3_pass<false>(MA, MB, g);
     for (int i = tid; i < g.nwords; i += kThreads) any_resid |= (MA[i] != 0);       // erosion result non-empty <=> opening non-empty
-    any_resid = __syncthreads_or(any_resid);
-    pt.tick();   // 13 open
+    any_resid = cta_sync_or(any_resid);
+    pt.tick();   // 12 open
     }
     if (!any_resid) {
         // nothing survives the opening: the detector returns None (indexing_ui.py:1559-1560)
@@ -417,12 +431,12 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     }
     // ---- P13: hole fill + per-component contour area filter ---------------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
-    __syncthreads();
+    cta_sync();
     R = ccl_build(sh.cs, MC, g, false, true, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     ccl_paint(MB, MB, g, ws, [](int root) { return root != 0; });
-    __syncthreads();
-    pt.tick();   // 14 defect hole fill
+    cta_sync();
+    pt.tick();   // 13 defect hole fill
     R = ccl_build(sh.cs, MB, g, true, false, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     {
@@ -435,7 +449,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             agg_add(ws.acc0(), valid, root, a2);
         }
     }
-    __syncthreads();
+    cta_sync();
     const long long min_area = a.p.min_area;
     long long max_area = (long long)__double2ll_rz(__dmul_rn((double)roi_area, a.p.max_area_frac));
     if (max_area < min_area) max_area = min_area;
@@ -449,15 +463,15 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         if (ws.parent()[i] == i && keep(i)) ++kept;
     const int n_kept = (int)cta_sum_u64(sh.cs, kept);
     ccl_paint(ME, nullptr, g, ws, keep);
-    __syncthreads();
-    pt.tick();   // 15 component area filter
+    cta_sync();
+    pt.tick();   // 14 component area filter
     // ---- P14: verdict ---------------------------------------------------------
     const unsigned defect_area = cta_popcount(sh.cs, ME, g);
     if (def_out) store_mask_bytes(ME, g, def_out);
     const int status = (n_kept > 0 && (long long)defect_area >= min_area) ? VI_STATUS_NG : VI_STATUS_OK;
     write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, n_kept > 0 ? defect_area : 0u, n_kept, status, dx, dy,
                  cx, cy, n_amb, n_runs_max);
-    pt.tick();   // 16 defect mask out + record
+    pt.tick();   // 15 defect mask out + record
 }
 
 __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_const
     const int n_total = a.n_images * a.n_units;
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
         process_unit(a, uid, smem, sh);
-        __syncthreads();
+        cta_sync();
     }
 }
 
