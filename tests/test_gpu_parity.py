@@ -137,6 +137,46 @@ def test_otsu_threshold(insp):
         assert t == R.otsu_threshold(im), i
 
 
+def test_otsu_threshold_near_ties(insp):
+    """Histograms whose between-class variance is flat or tied over many bins: the winner is decided by the
+    rounding of OpenCV's serial double recurrence (getThreshVal_Otsu_8u), which the GPU scan reproduces
+    -- also where it stops early (bins that cannot hold the maximum are never evaluated).  The checker is OpenCV's
+    own C++ scan (IPP dispatch off): on exactly tied histograms (mirror-symmetric ones) the closed-source IPP
+    routine the cv2 wheel dispatches to by default breaks the tie differently (tests/test_restate_vs_cv2.py states
+    both facts); everywhere else the two agree."""
+    import cv2
+    rng = np.random.default_rng(11)
+    p = vi_b200.default_params(gaussian_blur=0, morph_kernel=0)
+    cases = []
+    for _ in range(60):                                     # two spikes: every threshold between them ties exactly
+        a, b = sorted(rng.integers(0, 256, size=2))
+        n = int(rng.integers(1, 4000))
+        im = np.full(4200, a, np.uint8); im[:n] = b
+        cases.append(im.reshape(60, 70))
+    for _ in range(40):                                     # three / four spikes of random weights
+        v = np.sort(rng.choice(256, size=int(rng.integers(3, 5)), replace=False))
+        w = rng.random(len(v)); w /= w.sum()
+        cases.append(rng.choice(v, size=(50, 64), p=w).astype(np.uint8))
+    for _ in range(30):                                     # symmetric bimodal: near-ties around the middle
+        c = int(rng.integers(40, 216)); d = int(rng.integers(5, 40)); s = float(rng.uniform(0.5, 6))
+        half = np.clip(rng.normal(c - d, s, 1600), 0, 255).astype(np.uint8)
+        cases.append(np.concatenate([half, (2 * c - half.astype(int)).clip(0, 255).astype(np.uint8)]).reshape(40, 80))
+    for _ in range(20):                                     # sparse occupancy, long empty stretches
+        v = rng.choice(256, size=int(rng.integers(2, 12)), replace=False)
+        cases.append(rng.choice(v, size=(30, 41)).astype(np.uint8))
+    cases += [np.full((9, 9), 0, np.uint8), np.full((9, 9), 255, np.uint8), np.arange(256, dtype=np.uint8).reshape(16, 16),
+              np.array([[0, 255]], np.uint8), np.array([[7]], np.uint8), np.repeat(np.arange(0, 256, 5, dtype=np.uint8), 7).reshape(-1, 7)]
+    from oracle import restate as S
+    ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        for i, im in enumerate(cases):
+            _, t = insp.segment_cell(im, p, return_threshold=True)
+            assert t == R.otsu_threshold(im) == S.otsu_from_hist(np.bincount(im.ravel(), minlength=256)), (i, im.shape)
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+
+
 @pytest.mark.parametrize("cfg", [(6, 24, 20), (1, 8, 0), (40, 3, 5), (0, 24, 20), (6, 0, 0), (6, 255, 0), (200, 24, 20),
                                  (3, 12, 1)])
 def test_detect_defects(insp, cfg):

@@ -238,3 +238,29 @@ def test_full_unit_matches_cv2_arm():
             if d_ref is not None:
                 assert np.array_equal(d_ref, d_new)
                 assert np.array_equal(i1['roi'], i2['roi'])
+
+
+def test_otsu_exact_ties_follow_opencv_source_not_ipp():
+    """On mirror-symmetric histograms two thresholds tie exactly and rounding decides.  The restatement equals
+    OpenCV's C++ scan (IPP dispatch off) on every one of them; the closed-source IPP routine that the cv2 wheel
+    dispatches to by default (when present) may break such ties differently -- reported, not asserted."""
+    import cv2
+    from oracle import restate as S
+    rng = np.random.default_rng(11)
+    cases = []
+    for _ in range(150):
+        c = int(rng.integers(40, 216)); d = int(rng.integers(5, 40)); s = float(rng.uniform(0.5, 6))
+        half = np.clip(rng.normal(c - d, s, 1600), 0, 255).astype(np.uint8)
+        cases.append(np.concatenate([half, (2 * c - half.astype(int)).clip(0, 255).astype(np.uint8)]).reshape(40, 80))
+    ipp = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        for im in cases:
+            t = int(cv2.threshold(im, 0, 255, cv2.THRESH_BINARY_INV + cv2.THRESH_OTSU)[0])
+            assert S.otsu_from_hist(np.bincount(im.ravel(), minlength=256)) == t
+        cv2.ipp.setUseIPP(True)
+        diff = sum(S.otsu_from_hist(np.bincount(im.ravel(), minlength=256)) !=
+                   int(cv2.threshold(im, 0, 255, cv2.THRESH_BINARY_INV + cv2.THRESH_OTSU)[0]) for im in cases)
+        print(f"exactly tied histograms on which the IPP dispatch differs from OpenCV's own scan: {diff} of {len(cases)}")
+    finally:
+        cv2.ipp.setUseIPP(ipp)

@@ -197,7 +197,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         cta_sync();
         if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
             // default path: one histogram round on min(16, n_hist) warps
-            blur3_pass<true>(gray, g, hist_base + warp_id() * kHistWords, sh.hist, min(plan.n_hist, kWarps), nullptr, 0);
+            blur3_hist(gray, g, hist_base + warp_id() * kHistWords, min(plan.n_hist, kWarps));
             cta_sync();
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
             cta_sync();
