@@ -90,7 +90,7 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     p->band_pitch = 0;
     // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
     int cpitch = ((wmax + 2) / 3 + 2) & ~1;
-    int rch = wmax <= 96 ? 3 : wmax <= 224 ? 7 : wmax <= 352 ? 11 : 15;
+    int rch = wmax <= 352 ? 11 : 15;
     int band = wmax <= 480 ? 16 * (32 * rch + 2) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
     int otsu = 3 * 256 * 8 + 64;                // vi_pipeline.cuh: kOtsuWsBytes, at the end of the workspace
     band += otsu;                               // the Otsu warp works next to the rank-count cell pass

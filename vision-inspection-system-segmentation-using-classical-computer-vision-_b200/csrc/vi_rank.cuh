@@ -65,7 +65,7 @@ struct RankWs {
 // cs in uint2: one leading zero (the prefix "before column 0") + 32 * CH columns + one dummy column (written by
 // the V lanes that own no column), so no access needs a bounds test (a prefix only flows forward: what lies
 // past column w-1 is never read back).
-__host__ __device__ inline int rank_ch(int w) { return w <= 96 ? 3 : w <= 224 ? 7 : w <= 352 ? 11 : 15; }
+__host__ __device__ inline int rank_ch(int w) { return w <= 352 ? 11 : 15; }
 __host__ __device__ inline int rank_P(int w) { return 32 * rank_ch(w) + 2; }
 __host__ __device__ inline int rank_cpitch(int w) { return ((w + kCell - 1) / kCell + 2) & ~1; }      // cells + a dummy slot
 __host__ __device__ inline int rank_ws_bytes(int w) {
@@ -96,10 +96,11 @@ __device__ inline RankWs rank_ws_carve(unsigned char* base, int w, unsigned char
 __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int thr, const unsigned* ROI, unsigned* CAND,
                                        RankWs& w, int ci, int cj, unsigned cw);
 
-VI_PHASE void rank_tables(const int* lv, int thr, RankWs w) {
-    const int v = threadIdx.x;
-    if (v >= 256 && v < 256 + 49) {
-        const int e = v - 256, n179 = e / 7, n263 = e - n179 * 7;
+// Warp 0 only (the caller synchronises): the threshold table by bracket, the list counters, the zero column of cs.
+__device__ inline void rank_tables(const int* lv, int thr, RankWs w) {
+    const int lane = lane_id();
+    for (int e = lane; e < 49; e += 32) {
+        const int n179 = e / 7, n263 = e - n179 * 7;
         const int lo_idx = kLevels - n179;        // levels 0..lo_idx-1 surely have C <= 220: med >  LO
         const int hi_idx = kLevels - n263;        // level hi_idx surely has C >= 221:        med <= HI
         const int LO = lo_idx > 0 ? lv[lo_idx - 1] : -1;
@@ -110,8 +111,8 @@ VI_PHASE void rank_tables(const int* lv, int thr, RankWs w) {
         const int U3 = min(LO + thr + 1, 255);             // clean needs g <= U3
         w.table[e] = (unsigned)U1 | ((unsigned)U2 << 8) | ((unsigned)U3 << 16) | ((unsigned)U4 << 24);
     }
-    if (v >= 320 && v < 324) w.counters[v - 320] = 0;
-    if (v >= 352 && v < 352 + kLatBand) w.cs[(v - 352) * w.P] = make_uint2(0u, 0u);      // the prefix before column 0
+    if (lane < 4) w.counters[lane] = 0;
+    if (lane < kLatBand) w.cs[lane * w.P] = make_uint2(0u, 0u);      // the prefix before column 0
 }
 
 // Exact decision for one pixel: #(window <= g+thr) <= 220 or #(window <= g-thr-1) >= 221.
@@ -203,7 +204,7 @@ __device__ __forceinline__ void rank_row_cells(const Geom& g, RankWs& w, uint2* 
         const unsigned mmv = cm[i];
         const unsigned mn = mmv & 255u, mx = 255u - (mmv >> 8);
         const bool dirty = (i0 + lane < nlx) && (mn < ((cw >> 8) & 255u) || mx > ((cw >> 16) & 255u));
-    // append the dirty cells (one atomic per warp)
+        // append the dirty cells (one atomic per warp)
         const unsigned dm = __ballot_sync(kFull, dirty);
         if (dm) {
             int base = 0;
@@ -226,16 +227,17 @@ struct VBlk { unsigned B0, B1, mm; };
 constexpr unsigned kRep = 0x00100401u;
 constexpr unsigned kBit9 = 0x20080200u;
 
-__device__ __forceinline__ unsigned ind3(unsigned T, unsigned q0, unsigned q1, unsigned q2) {
-    const unsigned a = T - q0 * kRep, b = T - q1 * kRep, c = T - q2 * kRep;
+__device__ __forceinline__ unsigned ind3(unsigned T, unsigned x0, unsigned x1, unsigned x2) {     // x = q * kRep
+    const unsigned a = T - x0, b = T - x1, c = T - x2;
     const unsigned lo = (a ^ b ^ c) & kBit9, hi = ((a & b) | (c & (a | b))) & kBit9;
     return (lo + 2 * hi) >> 9;
 }
 
 __device__ __forceinline__ VBlk v_block(unsigned T0, unsigned T1, unsigned q0, unsigned q1, unsigned q2) {
     VBlk r;
-    r.B0 = ind3(T0, q0, q1, q2);
-    r.B1 = ind3(T1, q0, q1, q2);
+    const unsigned x0 = q0 * kRep, x1 = q1 * kRep, x2 = q2 * kRep;
+    r.B0 = ind3(T0, x0, x1, x2);
+    r.B1 = ind3(T1, x0, x1, x2);
     const unsigned mn = __vimin3_u32(q0, q1, q2), mx = __vimax3_u32(q0, q1, q2);
     r.mm = mn + ((255u - mx) << 16);
     return r;
@@ -356,9 +358,7 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
         for (int jj = warp; jj < j1 - j0; jj += kWarps) {
             uint2* row = w.cs + jj * w.P + 1;
             const unsigned short* cm = w.cmm + par * bufrows + jj * w.cpitch;
-            if (g.w <= 96) rank_row_cells<3>(g, w, row, cm, j0 + jj, nlx);
-            else if (g.w <= 224) rank_row_cells<7>(g, w, row, cm, j0 + jj, nlx);
-            else if (g.w <= 352) rank_row_cells<11>(g, w, row, cm, j0 + jj, nlx);
+            if (g.w <= 352) rank_row_cells<11>(g, w, row, cm, j0 + jj, nlx);
             else rank_row_cells<15>(g, w, row, cm, j0 + jj, nlx);
         }
         cta_sync();

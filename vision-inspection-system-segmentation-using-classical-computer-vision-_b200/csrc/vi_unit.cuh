@@ -63,10 +63,11 @@ VI_PHASE void prefetch_crop_l2(const KArgs& a, int uid) {
     }
 }
 
-VI_PHASE void select_levels(UnitShared& sh, int npix, int thr, int t) {
+// Warp 0 only (the caller synchronises).
+__device__ inline void select_levels(UnitShared& sh, int npix, int thr, int t) {
     // Six levels around the two Otsu class medians of the (blurred) histogram.
     // Any level set is exact; these make the cell brackets decide nearly every pixel.
-    if (warp_id() == 0) {
+    {
         const int lane = lane_id();
         unsigned c[8], tot = 0;
 #pragma unroll
@@ -106,7 +107,7 @@ VI_PHASE void select_levels(UnitShared& sh, int npix, int thr, int t) {
             sh.levels[3] = min(254, max(0, l3)); sh.levels[4] = min(254, max(0, l4)); sh.levels[5] = min(254, max(0, l5));
         }
     }
-    cta_sync();
+    __syncwarp();
 }
 
 __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, int otsu_t, unsigned seg_area,
@@ -219,17 +220,18 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         double* ows = reinterpret_cast<double*>(WS + plan.ws_bytes - kOtsuWsBytes);
         const bool lattice = (mode == MODE_FULL || mode == MODE_DETECT) && a.p.defect_method == 0 && g.w <= kRankMaxW &&
                              rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes;
-        if (warp_id() == 0) {
+        RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
+        if (warp_id() == 0) {                       // one warp, no barriers in between: approximate threshold, levels, tables
             int last;
             const int ta = otsu_approx_warp(sh.hist, npix, last);
             if (lane_id() == 0) { sh.t_apx = ta; sh.otsu_last = last; }
+            if (lattice) {
+                select_levels(sh, npix, a.p.threshold, ta);
+                rank_tables(sh.levels, a.p.threshold, rw);
+            }
         }
         cta_sync();
         if (lattice) {
-            select_levels(sh, npix, a.p.threshold, sh.t_apx);
-            RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
-            rank_tables(sh.levels, a.p.threshold, rw);
-            cta_sync();
             pt.tick();   // 2 approximate threshold, levels, tables
             rank_cells(gray, g, rw, sh.levels, sh.hist, npix, ows, sh.otsu_last, &sh.otsu_t, pt);
         } else {
