@@ -129,6 +129,34 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+# --------------------------------------------------------------------------- frame ingest (streaming kernels)
+def ingest_bench(insp, dev, n_img, peak, reps=10):
+    """The two frame-ingest kernels on n_img 4096x3000 frames: pure HBM streaming, reported against the
+    same measured copy bandwidth as the main kernel (algorithmic bytes: 4+1 and 2+1 per pixel)."""
+    import torch
+    out = {}
+    dst = torch.empty((n_img, H, W), dtype=torch.uint8, device=dev)
+    for name, shape, dtype, bpp, fn in (("argb32", (n_img, H, W, 4), torch.uint8, 5, insp.ingest_argb32),
+                                        ("gray16", (n_img, H, W), torch.int16, 3, insp.ingest_gray16)):
+        src = torch.empty(shape, dtype=dtype, device=dev)
+        src.view(torch.uint8).random_(0, 256)
+        for _ in range(3):
+            fn(src, out=dst)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn(src, out=dst)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = bpp * n_img * H * W / (ms * 1e-3) / 1e9
+        out[name] = {"ms_per_launch": ms, "frame_gpix_per_s": n_img * H * W / (ms * 1e-3) / 1e9, "achieved": gbs, "peak": peak,
+                     "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_px": bpp, "frames": n_img}
+        del src
+    return out
+
+
 # --------------------------------------------------------------------------- main arms
 def run_reference_arm(args, rank, world):
     if rank != 0:
@@ -260,6 +288,11 @@ def run_gpu_arm(args, rank, world, local_rank):
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak = 6650.0; peak_src = "fallback 6650 GB/s (of fallback)"
+        ingest = None
+        if world == 1 and not args.no_ingest:
+            del d_seg, d_def
+            torch.cuda.empty_cache()
+            ingest = ingest_bench(insp, dev, min(n_img, 64), peak)
         algo_bytes_per_launch = ALGO_BYTES_PER_PX * n_img * insp.unit_pixels
         achieved = algo_bytes_per_launch / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step per rank
         traffic = None
@@ -299,6 +332,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                     "h2d_note": "only frame rows covered by units are uploaded (full frames: %d B)" % (n_img * H * W),
                     "d2h_bytes_per_step": int(2 * total_px + n_img * n_units * 64)},
             "gpu_launches": args.steps,
+            "ingest": ingest,
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
@@ -316,6 +350,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic frames per GPU (tiled to --images)")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the reference arm (0 = host cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the frame-ingest streaming kernels")
     ap.add_argument("--cpu-passes", type=int, default=40, help="passes over the sample frames in the cpu_baseline leg (~10 s)")
     ap.add_argument("--ref-passes", type=int, default=8, help="passes over the sample frames per step of the reference arm")
     args = ap.parse_args()

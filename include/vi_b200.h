@@ -126,6 +126,19 @@ int vi_inspect_batch_host(vi_ctx* ctx, const uint8_t* h_frames, int n_images, in
  * unit covers are copied (one strided copy per merged row interval). */
 int64_t vi_host_upload_bytes(vi_ctx* ctx, int n_images, int64_t row_pitch);
 
+/* ---- frame ingest (device pointers, asynchronous on `stream`) ---------------- */
+
+/* segmentation.qimage_to_gray_array (segmentation.py:15-23) on the device: QImage ARGB32 frames (bytes B,G,R,A)
+ * to the mono uint8 frames vi_inspect_batch takes.  The reference reverses the colour channels before
+ * cv2.cvtColor(BGR2GRAY), so gray = (R*3735 + G*19235 + B*9798 + 16384) >> 15; identity on R=G=B.
+ * Pitches and strides in bytes.  HBM streaming: 4 B read + 1 B written per pixel. */
+int vi_ingest_argb32(vi_ctx* ctx, const uint8_t* d_bgra, int n_images, int W, int H, int64_t src_pitch,
+                     int64_t src_stride, uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, void* stream);
+/* ImageWidget.load_image's 16-bit rule (indexing_ui.py:153-155), (arr / 256).astype(uint8), on the device:
+ * little-endian uint16 frames to mono uint8 frames.  2 B read + 1 B written per pixel. */
+int vi_ingest_gray16(vi_ctx* ctx, const uint16_t* d_gray16, int n_images, int W, int H, int64_t src_pitch,
+                     int64_t src_stride, uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, void* stream);
+
 /* ---- per-unit compat entry points (host pointers, synchronous) ------------ */
 
 /* segmentation.segment_cell (segmentation.py:75-100): gray [h][w] -> mask 0/255. */

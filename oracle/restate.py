@@ -529,3 +529,16 @@ def detect_defects(gray, seg_mask, threshold=24, min_area=20, erode_px=6, levels
     if info is not None:
         info['n_kept'] = n_kept
     return out
+
+
+# --------------------------------------------------------------------------- frame ingest
+def gray_from_argb32(arr_bgra):
+    """Integer restatement of segmentation.py:20-23: OpenCV's 15-bit BGR2GRAY weights meet the reversed channels,
+    gray = (R*3735 + G*19235 + B*9798 + 16384) >> 15 with B,G,R the memory order of QImage ARGB32."""
+    b = arr_bgra[:, :, 0].astype(np.uint32); g = arr_bgra[:, :, 1].astype(np.uint32); r = arr_bgra[:, :, 2].astype(np.uint32)
+    return ((r * 3735 + g * 19235 + b * 9798 + 16384) >> 15).astype(np.uint8)
+
+
+def gray8_from_gray16(arr_u16):
+    """(arr / 256).astype(uint8) on uint16 == the high byte (indexing_ui.py:153-155)."""
+    return (arr_u16 >> 8).astype(np.uint8)

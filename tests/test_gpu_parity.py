@@ -363,6 +363,29 @@ def test_host_batch_equals_device_batch(insp, golden):
             assert rec_h[fi * 48 + i]['status'] == recs[i]['status']
 
 
+def test_frame_ingest(insp):
+    """Device ingest against the reference's host calls: aligned frames (vector kernels) and odd
+    shapes / pitches (scalar kernels), batch of frames, mono identity."""
+    import torch
+    rng = np.random.default_rng(9)
+    for n, H, W in ((3, 64, 4096), (2, 37, 131), (1, 5, 16), (1, 1, 1)):
+        a = rng.integers(0, 256, size=(n, H, W, 4), dtype=np.uint8)
+        if W >= 16:
+            a[0, 0, :8] = [[v, v, v, 255] for v in (0, 1, 127, 128, 254, 255, 17, 200)]
+        got = insp.ingest_argb32(torch.from_numpy(a).cuda()).cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], R.gray_from_argb32(a[i])), (n, H, W, i)
+        u = rng.integers(0, 65536, size=(n, H, W), dtype=np.uint16)
+        got = insp.ingest_gray16(torch.from_numpy(u.view(np.int16)).cuda()).cpu().numpy()
+        assert np.array_equal(got, R.gray8_from_gray16(u)), (n, H, W)
+    # a view with a row pitch wider than the frame (unaligned start: scalar kernel)
+    big = rng.integers(0, 256, size=(2, 40, 200, 4), dtype=np.uint8)
+    view = torch.from_numpy(big).cuda()[:, 3:35, 5:165]
+    got = insp.ingest_argb32(view).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(got[i], R.gray_from_argb32(big[i, 3:35, 5:165]))
+
+
 def test_fast_division_is_ieee(insp):
     """The Otsu recurrence divides through a precomputed reciprocal (two residual
     corrections); it must be the correctly rounded quotient, bit for bit."""

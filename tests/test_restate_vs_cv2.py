@@ -264,3 +264,22 @@ def test_otsu_exact_ties_follow_opencv_source_not_ipp():
         print(f"exactly tied histograms on which the IPP dispatch differs from OpenCV's own scan: {diff} of {len(cases)}")
     finally:
         cv2.ipp.setUseIPP(ipp)
+
+
+def test_ingest_restatements_equal_the_reference_calls():
+    """Frame ingest: the ARGB32 -> gray path of qimage_to_gray_array (channels reversed, then cv2's
+    BGR2GRAY) and the loader's 16-bit rule, restated in integers."""
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, size=(97, 131, 4), dtype=np.uint8)
+    assert np.array_equal(S.gray_from_argb32(a), R.gray_from_argb32(a))
+    # every gray level is a fixed point (mono frames pass through unchanged)
+    m = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 4, axis=2)
+    assert np.array_equal(R.gray_from_argb32(m)[0], np.arange(256, dtype=np.uint8))
+    assert np.array_equal(S.gray_from_argb32(m)[0], np.arange(256, dtype=np.uint8))
+    # channel extremes, where the R/B swap of the reference shows
+    ext = np.array([[[255, 0, 0, 255], [0, 255, 0, 255], [0, 0, 255, 255], [255, 255, 255, 0]]], np.uint8)
+    assert np.array_equal(S.gray_from_argb32(ext), R.gray_from_argb32(ext))
+    assert S.gray_from_argb32(ext)[0].tolist() == [76, 150, 29, 255]          # blue byte takes the red weight
+    u = rng.integers(0, 65536, size=(50, 70), dtype=np.uint16)
+    u[0, :4] = [0, 255, 256, 65535]
+    assert np.array_equal(S.gray8_from_gray16(u), R.gray8_from_gray16(u))

@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libvi_b200.so")
 SOURCES = [os.path.join(PKG_DIR, "csrc", "vi_api.cu")]
-HEADERS = [os.path.join(PKG_DIR, "csrc", n) for n in ("vi_device.cuh", "vi_ccl.cuh", "vi_pipeline.cuh", "vi_rank.cuh", "vi_canny.cuh", "vi_unit.cuh")]
+HEADERS = [os.path.join(PKG_DIR, "csrc", n) for n in ("vi_device.cuh", "vi_ccl.cuh", "vi_pipeline.cuh", "vi_rank.cuh", "vi_canny.cuh", "vi_unit.cuh", "vi_ingest.cuh")]
 HEADERS.append(os.path.join(ROOT, "include", "vi_b200.h"))
 
 NVCC_FLAGS = [

@@ -108,6 +108,41 @@ class Inspector:
             labels.data_ptr() if labels is not None else None, records.data_ptr(), C.c_void_p(st.cuda_stream)))
         return records, seg_masks, defect_masks
 
+    # ---- frame ingest (device) -------------------------------------------------------
+    def ingest_argb32(self, frames_bgra, out=None, stream=None):
+        """QImage ARGB32 frames (CUDA uint8 [n, H, W, 4], bytes B,G,R,A) -> mono CUDA uint8 [n, H, W], the reference's
+        `qimage_to_gray_array` (segmentation.py:15-23) for whole frames on the device."""
+        import torch
+        f = frames_bgra
+        if not f.is_cuda or f.dtype != torch.uint8 or f.dim() != 4 or f.shape[3] != 4 or f.stride(3) != 1 or f.stride(2) != 4:
+            raise TypeError("frames must be a CUDA uint8 tensor [n, H, W, 4] with packed pixels")
+        n, H, W, _ = f.shape
+        if out is None:
+            out = torch.empty((n, H, W), dtype=torch.uint8, device=f.device)
+        st = stream if stream is not None else torch.cuda.current_stream(f.device)
+        check(self._lib.vi_ingest_argb32(self._ctx, f.data_ptr(), int(n), int(W), int(H), int(f.stride(1)),
+                                         int(f.stride(0)) if n > 1 else int(f.stride(1)) * int(H), out.data_ptr(),
+                                         int(out.stride(1)), int(out.stride(0)) if n > 1 else int(out.stride(1)) * int(H),
+                                         C.c_void_p(st.cuda_stream)))
+        return out
+
+    def ingest_gray16(self, frames_u16, out=None, stream=None):
+        """16-bit mono frames (CUDA int16/uint16 [n, H, W]) -> mono CUDA uint8 with the reference's loader rule
+        `(arr / 256).astype(uint8)` (indexing_ui.py:153-155)."""
+        import torch
+        f = frames_u16
+        if not f.is_cuda or f.element_size() != 2 or f.dim() != 3 or f.stride(2) != 1:
+            raise TypeError("frames must be a CUDA 16-bit tensor [n, H, W]")
+        n, H, W = f.shape
+        if out is None:
+            out = torch.empty((n, H, W), dtype=torch.uint8, device=f.device)
+        st = stream if stream is not None else torch.cuda.current_stream(f.device)
+        check(self._lib.vi_ingest_gray16(self._ctx, f.data_ptr(), int(n), int(W), int(H), int(f.stride(1)) * 2,
+                                         (int(f.stride(0)) if n > 1 else int(f.stride(1)) * int(H)) * 2, out.data_ptr(),
+                                         int(out.stride(1)), int(out.stride(0)) if n > 1 else int(out.stride(1)) * int(H),
+                                         C.c_void_p(st.cuda_stream)))
+        return out
+
     def inspect_batch_host(self, frames: np.ndarray, params=None, want_masks=True, out=None):
         """frames: host uint8 [n, H, W] (numpy, ideally backed by pinned memory).
         Returns (records structured array, seg_masks u8[n*unit_px] | None, defect_masks | None)."""

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "vi_unit.cuh"
+#include "vi_ingest.cuh"
 
 using namespace vi;
 
@@ -636,4 +637,44 @@ extern "C" int vi_detect_defects(vi_ctx* c, const uint8_t* gray, const uint8_t* 
     if (found) *found = rec.n_kept > 0 ? 1 : 0;
     if (out_rec) *out_rec = rec;
     return VI_OK;
+}
+
+// ---------------------------------------------------------------------------
+// frame ingest (device pointers, asynchronous on `stream`)
+// ---------------------------------------------------------------------------
+static int ingest_common(vi_ctx* c, int fmt, const void* d_src, int n_images, int W, int H, int64_t src_pitch,
+                         int64_t src_stride, uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, void* stream) {
+    if (!c) return fail(VI_ERR_ARG, "ctx is null");
+    if (!d_src || !d_dst) return fail(VI_ERR_ARG, "ingest: null pointer");
+    const int bpp = fmt == 0 ? 4 : 2;
+    if (n_images <= 0 || W <= 0 || H <= 0) return fail(VI_ERR_ARG, "ingest: n_images=%d W=%d H=%d", n_images, W, H);
+    if (src_pitch < (int64_t)W * bpp || dst_pitch < W) return fail(VI_ERR_ARG, "ingest: pitch smaller than a row");
+    if (n_images > 1 && (src_stride < src_pitch * H || dst_stride < dst_pitch * H)) return fail(VI_ERR_ARG, "ingest: stride smaller than an image");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* src = (const uint8_t*)d_src;
+    const bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0) && src_pitch % 16 == 0 && src_stride % 16 == 0 &&
+                         dst_pitch % 16 == 0 && dst_stride % 16 == 0 && W % 16 == 0;
+    const int blocks = c->sm_count * 8;                 // 8 CTAs of 256 threads per SM: a full complement of warps
+    if (aligned) {
+        const long long n_items = (long long)n_images * H * (W / 16);
+        if (fmt == 0) ingest_argb32_v16<<<blocks, kIngestThreads, 0, st>>>(src, src_pitch, src_stride, d_dst, dst_pitch, dst_stride, W, H, n_items);
+        else ingest_gray16_v16<<<blocks, kIngestThreads, 0, st>>>(src, src_pitch, src_stride, d_dst, dst_pitch, dst_stride, W, H, n_items);
+    } else {
+        const long long n_px = (long long)n_images * H * W;
+        if (fmt == 0) ingest_argb32_scalar<<<blocks, kIngestThreads, 0, st>>>(src, src_pitch, src_stride, d_dst, dst_pitch, dst_stride, W, H, n_px);
+        else ingest_gray16_scalar<<<blocks, kIngestThreads, 0, st>>>(src, src_pitch, src_stride, d_dst, dst_pitch, dst_stride, W, H, n_px);
+    }
+    CU(cudaGetLastError());
+    return VI_OK;
+}
+
+extern "C" int vi_ingest_argb32(vi_ctx* c, const uint8_t* d_bgra, int n_images, int W, int H, int64_t src_pitch,
+                                int64_t src_stride, uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, void* stream) {
+    return ingest_common(c, 0, d_bgra, n_images, W, H, src_pitch, src_stride, d_gray, dst_pitch, dst_stride, stream);
+}
+
+extern "C" int vi_ingest_gray16(vi_ctx* c, const uint16_t* d_gray16, int n_images, int W, int H, int64_t src_pitch,
+                                int64_t src_stride, uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, void* stream) {
+    return ingest_common(c, 1, d_gray16, n_images, W, H, src_pitch, src_stride, d_gray, dst_pitch, dst_stride, stream);
 }
