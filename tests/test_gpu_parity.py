@@ -363,6 +363,61 @@ def test_host_batch_equals_device_batch(insp, golden):
             assert rec_h[fi * 48 + i]['status'] == recs[i]['status']
 
 
+def test_full_size_batch_properties(insp, golden):
+    """BASELINE configs[1] at its full size (64 frames of 4096x3000, 3,072 units) through size-independent
+    properties: the golden frame's units match the reference's outputs wherever the frame sits in the batch; copies of
+    a frame give identical records and masks (no state leaks between units or launches); a permuted batch gives the
+    permuted result; the host-buffer call equals the device call; NG counts equal the CPU oracle's."""
+    import torch
+    g = golden('config1')
+    boxes = [b for b, _ in g.boxes]
+    nu = len(boxes)
+    distinct = [g.frame(0)] + [synth.make_frame(s, boxes) for s in (1, 2, 3)]
+    order = [int(i) for i in np.random.default_rng(4).integers(0, 4, size=64)]
+    order[0], order[63] = 0, 0
+    frames = np.stack([distinct[i] for i in order])
+    insp.configure(Grid(boxes=g.boxes), is_reference=True)
+    d = torch.from_numpy(frames).cuda()
+    rec, seg, dfm = insp.inspect_batch(d)
+    torch.cuda.synchronize()
+    rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(64, nu)
+    seg = seg.cpu().numpy().reshape(64, -1)
+    dfm = dfm.cpu().numpy().reshape(64, -1)
+    first = {}
+    for k, i in enumerate(order):
+        if i not in first:
+            first[i] = k
+            continue
+        f = first[i]
+        for name in ('otsu_t', 'seg_area', 'roi_area', 'defect_area', 'n_kept', 'status', 'dx', 'dy', 'cx', 'cy'):
+            assert np.array_equal(rec[k][name], rec[f][name]), (k, name)
+        assert np.array_equal(seg[k], seg[f]) and np.array_equal(dfm[k], dfm[f]), k
+        assert (rec[k]['image'] == k).all() and (rec[k]['unit'] == np.arange(nu)).all()
+    # the golden frame (reference outputs) at both ends of the batch
+    seg_gold = g.masks('f0_seg')
+    dgold = g.defects(0, 6)
+    for k in (0, 63):
+        segs = insp.split_masks(seg[k]); defs = insp.split_masks(dfm[k])
+        for u in range(nu):
+            assert np.array_equal(segs[u], seg_gold[u]), (k, u)
+            ref = dgold[u] if dgold[u] is not None else np.zeros_like(defs[u])
+            assert np.array_equal(defs[u], ref), (k, u)
+    # NG counts of the other frames against the CPU oracle
+    for i in (1, 2, 3):
+        recs, _, _ = R.inspect_frame(distinct[i], g.boxes, R.Params(), (), None, True)
+        assert [int(r['status']) for r in recs] == rec[first[i]]['status'].tolist(), i
+    # permutation: reversed batch gives the reversed result
+    rec2, seg2, dfm2 = insp.inspect_batch(torch.flip(d, dims=[0]).contiguous())
+    torch.cuda.synchronize()
+    rec2 = rec2.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(64, nu)
+    assert np.array_equal(rec2['status'][::-1], rec['status']) and np.array_equal(rec2['defect_area'][::-1], rec['defect_area'])
+    assert np.array_equal(seg2.cpu().numpy().reshape(64, -1)[::-1], seg) and np.array_equal(dfm2.cpu().numpy().reshape(64, -1)[::-1], dfm)
+    # host-buffer call
+    hrec, hseg, hdef = insp.inspect_batch_host(frames)
+    assert np.array_equal(hseg.reshape(64, -1), seg) and np.array_equal(hdef.reshape(64, -1), dfm)
+    assert np.array_equal(hrec['status'].reshape(64, nu), rec['status']) and np.array_equal(hrec['image'].reshape(64, nu), rec['image'])
+
+
 def test_frame_ingest(insp):
     """Device ingest against the reference's host calls: aligned frames (vector kernels) and odd
     shapes / pitches (scalar kernels), batch of frames, mono identity."""
