@@ -127,6 +127,21 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
     cta_sync();
     if (pt) pt->acc(24);
     const int c8 = conn8 ? 1 : 0;
+    // Fast path: a stack of single runs, one per consecutive row, each touching the one above -- a solid blob, what
+    // a filled plate mask is -- is one component by inspection: every run points at run 1 and the union-find is skipped.
+    if (!border) {
+        int ok = 1;
+        for (int i = 2 + threadIdx.x; i <= (int)R; i += kThreads) {
+            const int y = ws.yy()[i], xs = ws.xs()[i], xe = ws.xe()[i];
+            ok &= (y == (int)ws.yy()[i - 1] + 1) && (xs <= (int)ws.xe()[i - 1] + c8) && (xe >= (int)ws.xs()[i - 1] - c8);
+        }
+        if (!cta_sync_or(!ok) && R > 0) {
+            for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) { ws.parent()[i] = 1; ws.acc0()[i] = 0; ws.acc1()[i] = 0; }
+            cta_sync();
+            if (pt) pt->acc(25);
+            return (int)R;
+        }
+    }
     // A: primary link = first overlapping run of the row above
     for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
         int y = ws.yy()[i];
