@@ -50,6 +50,28 @@ VI_PHASE void zero_bytes(uint8_t* __restrict__ dst, int n) {
     for (int e = head + (n16 << 4) + threadIdx.x; e < n; e += kThreads) dst[e] = 0;
 }
 
+// P14 for a sparse mask (the defect mask: a few blobs in a field of zeros): 128-bit zero fill of the whole unit, then only
+// the 4-pixel groups that hold a set pixel are written.  Needs w % 4 == 0 and a 4-byte aligned destination (else the
+// dense store runs).
+VI_PHASE void store_mask_bytes_sparse(const unsigned* M, const Geom& g, uint8_t* __restrict__ dst) {
+    if ((g.w & 3) != 0 || (reinterpret_cast<uintptr_t>(dst) & 3) != 0) { store_mask_bytes(M, g, dst); return; }
+    zero_bytes(dst, g.w * g.h);
+    cta_sync();                                              // the fill is ordered before the set groups below
+    const int qpr = g.w >> 2;
+    unsigned* d32 = reinterpret_cast<unsigned*>(dst);
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+        unsigned m = M[i];
+        if (m == 0) continue;
+        int y, c; word_rc(g, i, y, c);
+        unsigned* row = d32 + y * qpr + c * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned nib = (m >> (4 * k)) & 0xFu;
+            if (nib) row[k] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+        }
+    }
+}
+
 // L2 prefetch of a unit's crop rows (issued for the CTA's next unit while this one computes).
 VI_PHASE void prefetch_crop_l2(const KArgs& a, int uid) {
     const int img = uid / a.n_units, unit = uid - img * a.n_units;
@@ -469,7 +491,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     pt.tick();   // 14 component area filter
     // ---- P14: verdict ---------------------------------------------------------
     const unsigned defect_area = cta_popcount(sh.cs, ME, g);
-    if (def_out) store_mask_bytes(ME, g, def_out);
+    if (def_out) store_mask_bytes_sparse(ME, g, def_out);
     const int status = (n_kept > 0 && (long long)defect_area >= min_area) ? VI_STATUS_NG : VI_STATUS_OK;
     write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, n_kept > 0 ? defect_area : 0u, n_kept, status, dx, dy,
                  cx, cy, n_amb, n_runs_max);
