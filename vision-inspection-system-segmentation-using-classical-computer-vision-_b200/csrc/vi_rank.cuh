@@ -73,6 +73,7 @@ __host__ __device__ inline int rank_ws_bytes(int w) {
 }
 
 constexpr int kExactCap = 4096;
+constexpr int kExactWarpMax = 192;       // more ambiguous pixels than this: one thread per pixel instead of one warp
 __host__ __device__ inline long long rank_scratch_bytes(int wmax, int hmax) {
     return (long long)((wmax + kCell - 1) / kCell) * ((hmax + kCell - 1) / kCell) * 8 + kExactCap * 4;
 }
@@ -386,8 +387,36 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, int thr, 
     }
     cta_sync();
     pt.acc(22);
-    // ---- ambiguous pixels: exact rank counts, one warp per pixel -------------------------
+    // ---- ambiguous pixels: exact rank counts ------------------------------------------------
+    // Few of them (the usual case): one warp per pixel, 14 window pixels per lane.  Many (low thresholds, small
+    // units whose windows mostly straddle the plate edge): one thread per pixel walks its own window -- a quarter
+    // of the warp-instructions per pixel once the warps are full; the list is in cell order, so the lanes of a
+    // warp read neighbouring windows.
     const int ne = min(w.counters[1], w.exact_cap);
+    if (ne > kExactWarpMax) {
+        const int gp = g.gp;
+        for (int k2 = tid; k2 < ne; k2 += kThreads) {
+            const unsigned ent = w.exact[k2];
+            const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+            const int gv = gray[y * gp + x];
+            const int pa = gv + thr, pb = gv - thr - 1;
+            int ca = 0, cb = 0;
+            if (x >= 10 && x + 10 <= wm1 && y >= 10 && y + 10 <= hm1) {
+                const uint8_t* p = gray + (y - 10) * gp + (x - 10);
+                for (int dy = 0; dy < 21; ++dy) {
+#pragma unroll
+                    for (int dx = 0; dx < 21; ++dx) { const int v = p[dx]; ca += v <= pa; cb += v <= pb; }
+                    p += gp;
+                }
+            } else {
+                for (int dy = -10; dy <= 10; ++dy) {
+                    const uint8_t* row = gray + min(max(y + dy, 0), hm1) * gp;
+                    for (int dx = -10; dx <= 10; ++dx) { const int v = row[min(max(x + dx, 0), wm1)]; ca += v <= pa; cb += v <= pb; }
+                }
+            }
+            if (ca <= 220 || cb >= 221) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+        }
+    } else
     for (int k2 = warp; k2 < ne; k2 += kWarps) {
         const unsigned ent = w.exact[k2];
         const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
