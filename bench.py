@@ -307,7 +307,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             v, dt, ng_cpu = cpu_reference_run(uniq[:n_s], cores, args.cpu_passes)
             ng_gpu_s = int((rec['status'][:n_s * n_units] == vi_b200.STATUS_NG).sum())
             assert ng_cpu == ng_gpu_s * args.cpu_passes, f"NG count differs: cpu {ng_cpu} vs gpu {ng_gpu_s} x {args.cpu_passes}"
-            cpu = {"value": v, "unit": "units/s", "cores": cores, "kind": "port",
+            v1, dt1, _ = cpu_reference_run(uniq[:2], 1, 1)          # the reference as it really runs: one Python loop, one process
+            cpu = {"value": v, "unit": "units/s", "cores": cores, "kind": "port", "single_process_units_per_s": v1,
                    "sample": f"{n_s} of the same frames x 48 units x {args.cpu_passes} passes ({n_s * n_units * args.cpu_passes} "
                              f"units, {dt:.1f} s), {cores} processes x 1 cv2 thread, oracle/ref_cv2.py; NG count per pass "
                              f"equals the GPU's ({ng_gpu_s})"}

@@ -418,6 +418,35 @@ def test_full_size_batch_properties(insp, golden):
     assert np.array_equal(hrec['status'].reshape(64, nu), rec['status']) and np.array_equal(hrec['image'].reshape(64, nu), rec['image'])
 
 
+def test_ragged_grid_and_unaligned_frames(insp):
+    """A grid JSON may hold arbitrary boxes (indexing_ui.py:2881-2889): units of different sizes in one batch, on
+    frames whose width is not a multiple of 16 (the scalar gather), with exclusions and a centroid shift, against the
+    cv2 oracle unit by unit."""
+    import torch
+    boxes = [((7, 5, 316, 315), 0), ((340, 9, 200, 150), 1), ((560, 20, 96, 96), 2), ((700, 3, 40, 33), 3),
+             ((760, 50, 13, 21), 4), ((340, 170, 333, 120), 5), ((800, 100, 150, 230), 6), ((690, 60, 3, 3), 7)]
+    W, H = 1001, 345
+    frames = np.stack([synth.make_frame(s, [b for b, _ in boxes], H=H, W=W, inset=6, jitter=2) for s in (11, 12)])
+    excl = [{'shape': 'rect', 'x': 20, 'y': 10, 'w': 30, 'h': 12}, {'shape': 'circle', 'cx': 60, 'cy': 50, 'r': 9}]
+    for params in (dict(), dict(erode_px=2, threshold=10, min_area=3)):
+        recs0, _, _ = R.inspect_frame(frames[0], boxes, R.Params(**params), excl, None, True)
+        refc = {i: (r['cx'], r['cy']) for i, r in enumerate(recs0) if r['cx'] == r['cx']}
+        insp.configure(Grid(boxes=boxes, exclusions=excl, ref_centroids=refc), is_reference=False)
+        rec, seg, dfm = insp.inspect_batch(torch.from_numpy(frames).cuda(), vi_b200.default_params(**params))
+        torch.cuda.synchronize()
+        rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(2, len(boxes))
+        seg = seg.cpu().numpy().reshape(2, -1); dfm = dfm.cpu().numpy().reshape(2, -1)
+        for fi in range(2):
+            recs, osegs, odefs = R.inspect_frame(frames[fi], boxes, R.Params(**params), excl, refc, False)
+            segs = insp.split_masks(seg[fi]); defs = insp.split_masks(dfm[fi])
+            for u, o in enumerate(recs):
+                assert np.array_equal(segs[u], osegs[u]), (params, fi, u, 'seg')
+                ref = odefs[u] if odefs[u] is not None else np.zeros_like(defs[u])
+                assert np.array_equal(defs[u], ref), (params, fi, u, 'defect')
+                for k in ('seg_area', 'roi_area', 'defect_area', 'n_kept', 'status', 'dx', 'dy'):
+                    assert rec[fi, u][k] == o[k], (params, fi, u, k, rec[fi, u][k], o[k])
+
+
 def test_frame_ingest(insp):
     """Device ingest against the reference's host calls: aligned frames (vector kernels) and odd
     shapes / pitches (scalar kernels), batch of frames, mono identity."""

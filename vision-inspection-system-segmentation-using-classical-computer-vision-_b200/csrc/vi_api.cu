@@ -150,9 +150,15 @@ static int set_grid_state(vi_ctx* c, GridState& gs, const int32_t* r, int n, cud
         gs.hmax = std::max(gs.hmax, h);
     }
     gs.unit_px = gs.off[n];
-    if (!make_plan(gs.wmax, gs.hmax, c->smem_optin, c->smem_static, &gs.plan))
-        return fail(VI_ERR_TOO_LARGE, "grid: a %dx%d unit does not fit the %d-byte shared-memory-resident path", gs.wmax,
-                    gs.hmax, c->smem_optin);
+    int gray_need = 0, words_need = 0;
+    for (int i = 0; i < n; ++i) {
+        const Geom g = make_geom(gs.rects[i].z, gs.rects[i].w);
+        gray_need = std::max(gray_need, g.gp * g.h);
+        words_need = std::max(words_need, g.nwords);
+    }
+    if (!make_plan(gs.wmax, gs.hmax, c->smem_optin, c->smem_static, &gs.plan, gray_need, words_need))
+        return fail(VI_ERR_TOO_LARGE, "grid: its largest units (up to %d wide, %d high, %d crop bytes) do not fit the %d-byte "
+                    "shared-memory-resident path", gs.wmax, gs.hmax, gray_need, c->smem_optin);
     int rc;
     if ((rc = gs.d_rects.ensure(sizeof(int4) * n))) return rc;
     if ((rc = gs.d_off.ensure(sizeof(long long) * (n + 1)))) return rc;

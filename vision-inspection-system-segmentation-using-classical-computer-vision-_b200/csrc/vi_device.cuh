@@ -83,10 +83,12 @@ struct SmemPlan {
 
 __host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
 
-__host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, SmemPlan* p) {
+// gray_need / mask_words_need: the largest crop and the largest bit mask over the grid's units (a ragged grid's widest
+// and tallest units need not be the same one); 0 = take them from a wmax x hmax unit.
+__host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, SmemPlan* p, int gray_need = 0, int mask_words_need = 0) {
     Geom g = make_geom(wmax, hmax);
-    p->gray_bytes = align16(g.gp * hmax);
-    p->mask_bytes = align16(g.nwords * 4);
+    p->gray_bytes = align16(gray_need > 0 ? gray_need : g.gp * hmax);
+    p->mask_bytes = align16((mask_words_need > 0 ? mask_words_need : g.nwords) * 4);
     p->band_pitch = 0;
     // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
     int cpitch = ((wmax + 2) / 3 + 2) & ~1;
