@@ -114,6 +114,12 @@ int vi_inspect_batch(vi_ctx* ctx, const uint8_t* d_frames, int n_images, int W, 
                      uint8_t* d_seg_masks, uint8_t* d_defect_masks, int32_t* d_labels_or_null,
                      vi_unit_record* d_records, void* stream);
 
+/* Optional extra output of subsequent vi_inspect_batch calls: per (image, unit) the area, sum of x and sum of y of
+ * the final segmentation mask (after exclusions) -- what segmentation.mask_stats returns for the exported
+ * mask_%04d.png in export_masks_and_csv (indexing_ui.py:2716-2722; the caller divides in double, as numpy's mean
+ * does).  d_stats: device, int64 [n_images*n_units][3]; NULL switches it off. */
+int vi_set_seg_stats_output(vi_ctx* ctx, int64_t* d_stats);
+
 /* Same, from and to HOST buffers (pinned memory recommended): uploads frames in
  * chunks, overlaps copy and compute on internal streams, downloads masks and
  * records; blocks until done.  h_seg_masks / h_defect_masks may be NULL to skip

@@ -447,6 +447,42 @@ def test_ragged_grid_and_unaligned_frames(insp):
                     assert rec[fi, u][k] == o[k], (params, fi, u, k, rec[fi, u][k], o[k])
 
 
+def test_seg_stats_output_matches_mask_stats(insp, golden, tmp_path):
+    """The optional per-unit (area, sum x, sum y) of the final seg masks against the reference's
+    mask_stats on the masks themselves, and the CSV rows built from it against rows built the reference's way."""
+    import csv
+    import torch
+    from vi_b200 import export
+    g = golden('config4')
+    meta = g.meta
+    refc = {i: (float(c[0]), float(c[1])) for i, c in enumerate(g.z['ref_centroids']) if not np.isnan(c[0])}
+    insp.configure(Grid(boxes=g.boxes, exclusions=meta['exclusions'], ref_centroids=refc), is_reference=False)
+    d = torch.from_numpy(g.frame(1)[None]).cuda()
+    stats = torch.full((len(g.boxes), 3), -1, dtype=torch.int64, device='cuda')
+    rec, seg, _ = insp.inspect_batch(d, seg_stats=stats)
+    torch.cuda.synchronize()
+    segs = insp.split_masks(seg.cpu().numpy())
+    rows = export.masks_summary_rows(stats.cpu().numpy())
+    rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    for i, m in enumerate(segs):
+        st = R.mask_stats(m)
+        assert rows[i]['area'] == st['area'] == rec[i]['seg_area']
+        assert (rows[i]['centroid_x'], rows[i]['centroid_y']) == st['centroid'], i
+    export.write_masks_summary_csv(str(tmp_path / 'a.csv'), rows)
+    with open(tmp_path / 'b.csv', 'w', newline='') as cf:                    # indexing_ui.py:2723-2729 on mask_stats rows
+        w = csv.DictWriter(cf, fieldnames=['index', 'mask', 'area', 'centroid_x', 'centroid_y'])
+        w.writeheader()
+        for i, m in enumerate(segs):
+            st = R.mask_stats(m)
+            w.writerow({'index': i, 'mask': f'mask_{i:04d}.png', 'area': st['area'], 'centroid_x': st['centroid'][0], 'centroid_y': st['centroid'][1]})
+    assert (tmp_path / 'a.csv').read_bytes() == (tmp_path / 'b.csv').read_bytes()
+    # switched off again: the buffer stays untouched
+    stats.fill_(-7)
+    insp.inspect_batch(d)
+    torch.cuda.synchronize()
+    assert (stats == -7).all()
+
+
 def test_frame_ingest(insp):
     """Device ingest against the reference's host calls: aligned frames (vector kernels) and odd
     shapes / pitches (scalar kernels), batch of frames, mono identity."""

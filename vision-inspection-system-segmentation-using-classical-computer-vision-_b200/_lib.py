@@ -35,7 +35,7 @@ EXPORTS = [
     "vi_last_error", "vi_version", "vi_params_default", "vi_ctx_create", "vi_ctx_destroy", "vi_set_grid",
     "vi_set_exclusions", "vi_set_ref_centroids", "vi_unit_pixels", "vi_unit_offsets", "vi_inspect_batch",
     "vi_inspect_batch_host", "vi_host_upload_bytes", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
-    "vi_label_components", "vi_detect_defects", "vi_ingest_argb32", "vi_ingest_gray16", "vi_debug_set_profile", "vi_debug_fastdiv_check", "vi_debug_adaptive_taps",
+    "vi_label_components", "vi_detect_defects", "vi_ingest_argb32", "vi_ingest_gray16", "vi_set_seg_stats_output", "vi_debug_set_profile", "vi_debug_fastdiv_check", "vi_debug_adaptive_taps",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load():
     lib.vi_debug_fastdiv_check.argtypes = [vp, i64, C.c_uint64, P(i64)]
     lib.vi_detect_defects.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(ViParams), vp, P(i32), vp]
     lib.vi_debug_adaptive_taps.argtypes = [C.c_int, vp]
+    lib.vi_set_seg_stats_output.argtypes = [vp, vp]
     lib.vi_ingest_argb32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, vp, i64, i64, vp]
     lib.vi_ingest_gray16.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, vp, i64, i64, vp]
     for n in EXPORTS:

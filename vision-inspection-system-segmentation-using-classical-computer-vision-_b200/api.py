@@ -81,7 +81,7 @@ class Inspector:
 
     # ---- batch calls -------------------------------------------------------------
     def inspect_batch(self, frames, params=None, seg_masks=None, defect_masks=None, records=None, labels=None,
-                      stream=None):
+                      stream=None, seg_stats=None):
         """frames: CUDA uint8 tensor [n, H, W] (row stride may exceed W).  Returns
         (records, seg_masks, defect_masks) as CUDA tensors (records: uint8 [n*units, 64]);
         asynchronous on `stream` (default: torch's current stream)."""
@@ -101,6 +101,8 @@ class Inspector:
             records = torch.empty((n * self.n_units, 64), dtype=torch.uint8, device=dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         p = params if params is not None else default_params()
+        # seg_stats: optional CUDA int64 [n*units, 3] (area, sum x, sum y of each final seg mask: the CSV export's numbers)
+        check(self._lib.vi_set_seg_stats_output(self._ctx, seg_stats.data_ptr() if seg_stats is not None else None))
         check(self._lib.vi_inspect_batch(
             self._ctx, frames.data_ptr(), int(n), int(W), int(H), int(frames.stride(1)),
             int(frames.stride(0)) if n > 1 else int(frames.stride(1)) * int(H),

@@ -82,6 +82,7 @@ struct vi_ctx {
     cudaStream_t streams[kHostSlots] = {};
     int smem_set = 0;
     long long* prof = nullptr;
+    long long* seg_stats = nullptr;
 };
 
 extern "C" const char* vi_last_error(void) { return g_err.c_str(); }
@@ -258,6 +259,12 @@ extern "C" int vi_debug_set_profile(vi_ctx* c, long long* d_cycles) {
     return VI_OK;
 }
 
+extern "C" int vi_set_seg_stats_output(vi_ctx* c, int64_t* d_stats) {
+    if (!c) return fail(VI_ERR_ARG, "ctx is null");
+    c->seg_stats = (long long*)d_stats;
+    return VI_OK;
+}
+
 extern "C" int64_t vi_host_upload_bytes(vi_ctx* c, int n_images, int64_t row_pitch) {
     if (!c) return 0;
     std::vector<std::pair<int, int>> iv;
@@ -421,6 +428,7 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     a.wmax = gs.wmax; a.hmax = gs.hmax;
     a.plan = gs.plan;
     a.prof = (&gs == &c->grid) ? c->prof : nullptr;
+    if (&gs != &c->grid) a.seg_stats = nullptr;
     if (c->smem_set < gs.plan.total) {
         CU(cudaFuncSetAttribute(vi_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
         c->smem_set = c->smem_optin - c->smem_static;
@@ -469,6 +477,7 @@ extern "C" int vi_inspect_batch(vi_ctx* c, const uint8_t* d_frames, int n_images
     a.is_reference = c->is_reference;
     a.seg_out = d_seg; a.def_out = d_def; a.labels_out = d_labels; a.rec = d_rec;
     a.mode = MODE_FULL;
+    a.seg_stats = c->seg_stats;
     return launch_units(c, a, c->grid, (cudaStream_t)stream);
 }
 

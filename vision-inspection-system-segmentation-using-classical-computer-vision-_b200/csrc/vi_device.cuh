@@ -154,6 +154,7 @@ struct KArgs {
     long long scratch_f32_off;      // offset of the float plane inside a CTA's scratch (adaptive threshold only)
     long long scratch_rank_off;     // offset of the rank-count lists (dirty cells, ambiguous pixels)
     int wmax, hmax;
+    long long* seg_stats;           // optional: [n_total][3] area, sum x, sum y of the final seg mask (CSV export), or null
     long long* prof;                // diagnostics: [n_total][32] per-phase cycle counts, or null
     SmemPlan plan;
 };

@@ -132,6 +132,21 @@ __device__ inline void select_levels(UnitShared& sh, int npix, int thr, int t) {
     __syncwarp();
 }
 
+// Area and coordinate sums of a bit mask (segmentation.mask_stats, segmentation.py:103-111: the caller divides).
+__device__ inline void mask_sums(CtaScratch& cs, const unsigned* M, const Geom& g, long long* out3) {
+    unsigned long long n = 0, sx = 0, sy = 0;
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+        int y, c; word_rc(g, i, y, c);
+        const unsigned m = M[i];
+        const unsigned pc = __popc(m);
+        const unsigned pos = __popc(m & 0xAAAAAAAAu) + 2 * __popc(m & 0xCCCCCCCCu) + 4 * __popc(m & 0xF0F0F0F0u) +
+                             8 * __popc(m & 0xFF00FF00u) + 16 * __popc(m & 0xFFFF0000u);
+        n += pc; sx += (unsigned long long)pc * (c * 32) + pos; sy += (unsigned long long)pc * y;
+    }
+    n = cta_sum_u64(cs, n); sx = cta_sum_u64(cs, sx); sy = cta_sum_u64(cs, sy);
+    if (threadIdx.x == 0) { out3[0] = (long long)n; out3[1] = (long long)sx; out3[2] = (long long)sy; }
+}
+
 __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, int otsu_t, unsigned seg_area,
                                     unsigned roi_area, unsigned defect_area, int n_kept, int status, int dx, int dy,
                                     double cx, double cy, int n_amb, int n_runs) {
@@ -328,6 +343,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             }
             // ---- P8: seg mask out -------------------------------------------------
             seg_area = cta_popcount(sh.cs, MA, g);
+            if (a.seg_stats) mask_sums(sh.cs, MA, g, a.seg_stats + (long long)uid * 3);     // CSV export's mask_stats, optional
             if (seg_out) store_mask_bytes(MA, g, seg_out);
             pt.tick();   // 8 exclusions + seg mask out
             if (mode == MODE_SEG_ONLY) {
@@ -351,17 +367,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         return;
     }
     if (mode == MODE_STATS) {
-        unsigned long long n = 0, sx = 0, sy = 0;
-        for (int i = tid; i < g.nwords; i += kThreads) {
-            int y, c; word_rc(g, i, y, c);
-            unsigned m = MA[i];
-            unsigned pc = __popc(m);
-            unsigned pos = __popc(m & 0xAAAAAAAAu) + 2 * __popc(m & 0xCCCCCCCCu) + 4 * __popc(m & 0xF0F0F0F0u) +
-                           8 * __popc(m & 0xFF00FF00u) + 16 * __popc(m & 0xFFFF0000u);
-            n += pc; sx += (unsigned long long)pc * (c * 32) + pos; sy += (unsigned long long)pc * y;
-        }
-        n = cta_sum_u64(sh.cs, n); sx = cta_sum_u64(sh.cs, sx); sy = cta_sum_u64(sh.cs, sy);
-        if (tid == 0) { stats[0] = (long long)n; stats[1] = (long long)sx; stats[2] = (long long)sy; }
+        mask_sums(sh.cs, MA, g, stats);
         return;
     }
     if (mode == MODE_ERODE) {
