@@ -290,10 +290,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
                 adaptive_threshold(g_blur, g, a.adapt_bs, a.ataps, a.p.adapt_C, reinterpret_cast<float*>(gs + a.scratch_f32_off), MA);
             else if (src_mode == 0) blur_pass<0, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             else if (src_mode == 1) {
-                threshold_gray(gray, g, MB, otsu_t);
+                threshold_gray(gray, g, MB, otsu_t, sh.misc);
                 cta_sync();
                 pt.acc(29);
-                threshold_band(gray, g, MB, MA, MC, otsu_t);
+                threshold_band(gray, g, MB, MA, MC, otsu_t, MD, 2 * (plan.mask_bytes / 4), sh.misc);
             }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             cta_sync();
