@@ -108,7 +108,7 @@ extern "C" int vi_ctx_create(int device, vi_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, vi_unit_kernel));
+    CU(cudaFuncGetAttributes(&fa, vi_unit_kernel<false>));
     c->smem_static = ((int)fa.sharedSizeBytes + 15) & ~15;
     for (auto& s : c->streams) {
         cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -430,11 +430,13 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     a.prof = (&gs == &c->grid) ? c->prof : nullptr;
     if (&gs != &c->grid) a.seg_stats = nullptr;
     if (c->smem_set < gs.plan.total) {
-        CU(cudaFuncSetAttribute(vi_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
+        CU(cudaFuncSetAttribute(vi_unit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
+        CU(cudaFuncSetAttribute(vi_unit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
         c->smem_set = c->smem_optin - c->smem_static;
     }
     if (gs.plan.total > c->smem_set) return fail(VI_ERR_TOO_LARGE, "shared-memory plan %d > %d", gs.plan.total, c->smem_set);
-    vi_unit_kernel<<<nblocks, kThreads, gs.plan.total, stream>>>(a);
+    if (a.prof) vi_unit_kernel<true><<<nblocks, kThreads, gs.plan.total, stream>>>(a);       // diagnostics build: phase timers
+    else vi_unit_kernel<false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);
     CU(cudaGetLastError());
     return VI_OK;
 }

@@ -89,8 +89,9 @@ __device__ __forceinline__ void run_edges(const unsigned* M, const Geom& g, int 
 
 // Builds runs + components of mask M.  ws_s (shared) is used when the runs fit,
 // else ws_g (global scratch).  Returns R (run count) and the workspace used.
+template <class PT>
 VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
-                                const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PhaseTimer* pt = nullptr) {
+                       const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PT* pt) {
     const int per = (g.nwords + kThreads - 1) / kThreads;
     const int i0 = threadIdx.x * per;
     const int i1 = min(i0 + per, g.nwords);

@@ -175,13 +175,18 @@ struct CtaScratch {
 // that ends the phase), written only when KArgs::prof is set.
 constexpr int kProfSlots = 32;
 struct PtState { long long* out; long long t; int k; int pad; };      // lives in shared memory: no registers held across phases
-struct PhaseTimer {
+// ON = false compiles every hook away (the production kernel); ON = true is the diagnostics kernel that
+// vi_debug_set_profile selects.
+template <bool ON>
+struct PhaseTimerT {
     PtState* s;
     __device__ __forceinline__ void start(PtState* st, long long* o) {
+        if (!ON) return;
         s = st;
         if (threadIdx.x == 0) { s->out = o; s->k = 0; if (o) s->t = clock64(); }
     }
     __device__ __forceinline__ void tick() {
+        if (!ON) return;
         if (threadIdx.x == 0 && s->out) {
             const long long n = clock64();
             const int k = s->k;
@@ -191,6 +196,7 @@ struct PhaseTimer {
     }
     // sub-phase accounting: add the time since the last tick/acc to `slot` without consuming a phase slot
     __device__ __forceinline__ void acc(int slot) {
+        if (!ON) return;
         if (threadIdx.x == 0 && s->out) { const long long n = clock64(); s->out[slot] += n - s->t; s->t = n; }
     }
 };

@@ -292,8 +292,9 @@ __device__ __forceinline__ void v_band(VState& st, unsigned T0, unsigned T1, con
 // The warp kOtsuWarp carries the exact Otsu scan along when it owns no column: q1 sums and reciprocals during the
 // first band, a slice of the mu1 recurrence during each further band, the rest at the end; *otsu_t holds the
 // threshold on return.
+template <class PT>
 VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, const unsigned* hist, int npix,
-                         double* ows, int olast, int* otsu_t, PhaseTimer& pt) {
+                         double* ows, int olast, int* otsu_t, PT& pt) {
     const int lane = lane_id(), warp = warp_id();
     const int nly = (g.h + kCell - 1) / kCell, nlx = (g.w + kCell - 1) / kCell;
     const int hm1 = g.h - 1;
@@ -375,8 +376,9 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
 
 // Part 2 (needs the ROI): CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
 // Returns the number of pixels that needed an exact rank count.
+template <class PT>
 VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, int thr, const unsigned* ROI, unsigned* CAND,
-                         PhaseTimer& pt) {
+                         PT& pt) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const int hm1 = g.h - 1, wm1 = g.w - 1;
     // ---- dirty cells: per-pixel classification ----------------------------------------

@@ -159,6 +159,7 @@ __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, 
     }
 }
 
+template <bool PROF>
 __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitShared& sh) {
     const int tid = threadIdx.x;
     const int img = uid / a.n_units, unit = uid - img * a.n_units;
@@ -197,7 +198,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     const uint8_t* aux = a.aux_mask ? a.aux_mask + moff : nullptr;
     long long* stats = a.stats_out ? a.stats_out + (long long)uid * 8 : nullptr;
 
-    PhaseTimer pt;
+    PhaseTimerT<PROF> pt;
     pt.start(&sh.pt, a.prof ? a.prof + (long long)uid * kProfSlots : nullptr);
     const bool need_gray = mode == MODE_FULL || mode == MODE_SEG_ONLY || mode == MODE_DETECT;
     const bool need_seg = mode == MODE_FULL || mode == MODE_SEG_ONLY;
@@ -504,6 +505,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     pt.tick();   // 15 defect mask out + record
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ UnitShared sh_raw;
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_const
     UnitShared& sh = *shp;
     const int n_total = a.n_images * a.n_units;
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
-        process_unit(a, uid, smem, sh);
+        process_unit<PROF>(a, uid, smem, sh);
         cta_sync();
     }
 }
