@@ -128,6 +128,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
     cta_sync();
     if (pt) pt->acc(24);
     const int c8 = conn8 ? 1 : 0;
+    if (threadIdx.x == 0) cs.flag = 0;
     // Fast path: a stack of single runs, one per consecutive row, each touching the one above -- a solid blob, what
     // a filled plate mask is -- is one component by inspection: every run points at run 1 and the union-find is skipped.
     if (!border) {
@@ -138,6 +139,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
         }
         if (!cta_sync_or(!ok) && R > 0) {
             for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) { ws.parent()[i] = 1; ws.acc0()[i] = 0; ws.acc1()[i] = 0; }
+            if (threadIdx.x == 0) cs.flag = 1;             // one component: ccl_largest sums it directly
             cta_sync();
             if (pt) pt->acc(25);
             return (int)R;
@@ -246,6 +248,17 @@ VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
                                   unsigned& area, unsigned long long& sum_x, unsigned long long& sum_y) {
     area = 0; sum_x = 0; sum_y = 0;
     if (R == 0) return 0;
+    if (cs.flag) {                                  // ccl_build found a single solid component (root = run 1)
+        unsigned long long a = 0, sx = 0, sy = 0;
+        for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {
+            const unsigned long long xs = ws.xs()[i], xe = ws.xe()[i], len = xe - xs + 1;
+            a += len; sx += (xs + xe) * len / 2; sy += (unsigned long long)ws.yy()[i] * len;
+        }
+        area = (unsigned)cta_sum_u64(cs, a);
+        sum_x = cta_sum_u64(cs, sx);
+        sum_y = cta_sum_u64(cs, sy);
+        return 1;
+    }
     const int Rpad = (R + kThreads - 1) / kThreads * kThreads;
     for (int base = 0; base < Rpad; base += kThreads) {
         int i = base + threadIdx.x + 1;
