@@ -145,6 +145,21 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
             return (int)R;
         }
     }
+    // Fast path of the hole fill: when every background run touches the crop border itself there is no hole (what the
+    // background of a sparse defect mask, or of a plate without bright inclusions, looks like): all runs join node 0.
+    if (border) {
+        int inner = 0;
+        for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
+            const int y = ws.yy()[i];
+            inner |= !(y == 0 || y == g.h - 1 || ws.xs()[i] == 0 || (int)ws.xe()[i] == g.w - 1);
+        }
+        if (!cta_sync_or(inner)) {
+            for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) { ws.parent()[i] = 0; ws.acc0()[i] = 0; ws.acc1()[i] = 0; }
+            cta_sync();
+            if (pt) pt->acc(25);
+            return (int)R;
+        }
+    }
     // A: primary link = first overlapping run of the row above
     for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) {
         int y = ws.yy()[i];
