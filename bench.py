@@ -195,6 +195,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     from vi_b200.grid import Grid
     dist = None
     if world > 1:
+        # NCCL's version banner goes to stdout when NCCL_DEBUG is VERSION: stdout carries the JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
