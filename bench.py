@@ -29,6 +29,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (set on the GPU boxes) and at WARN: stdout carries
+# the JSON line only, so that level is dropped before torch / NCCL are loaded (INFO and above are left alone).
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
 
 import numpy as np
 
@@ -195,9 +199,6 @@ def run_gpu_arm(args, rank, world, local_rank):
     from vi_b200.grid import Grid
     dist = None
     if world > 1:
-        # NCCL's version banner goes to stdout when NCCL_DEBUG is VERSION: stdout carries the JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
