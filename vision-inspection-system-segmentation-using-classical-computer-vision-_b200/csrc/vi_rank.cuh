@@ -137,15 +137,31 @@ __device__ inline bool rank_exact_pixel_thread(const uint8_t* gray, const Geom& 
 __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int thr, const unsigned* ROI, unsigned* CAND,
                                        RankWs& w, int ci, int cj, unsigned cw) {
     const unsigned u1 = cw & 255u, u2 = (cw >> 8) & 255u, u3 = (cw >> 16) & 255u, u4 = cw >> 24;
+    // most dirty cells (plate edges, bright field) lie outside the ROI: three ROI bits per row decide that first
+    const int x0 = ci * kCell, c0 = x0 >> 5, sh = x0 & 31;
+    unsigned roi3[kCell];
+    unsigned any = 0;
+#pragma unroll
+    for (int rr = 0; rr < kCell; ++rr) {
+        const int y = min(cj * kCell + rr, g.h - 1);
+        const unsigned* row = ROI + y * g.wpr;
+        unsigned b = row[c0] >> sh;
+        if (sh > 29 && c0 + 1 < g.wpr) b |= row[c0 + 1] << (32 - sh);
+        roi3[rr] = (cj * kCell + rr < g.h) ? (b & 7u) : 0u;          // bits past the crop edge are 0 in every mask
+        any |= roi3[rr];
+    }
+    if (!any) return;
+#pragma unroll
     for (int rr = 0; rr < kCell; ++rr) {
         const int y = cj * kCell + rr;
         if (y >= g.h) break;
+#pragma unroll
         for (int cc = 0; cc < kCell; ++cc) {
             const int x = ci * kCell + cc;
             if (x >= g.w) break;
             const int wi = y * g.wpr + (x >> 5);
             const unsigned bit = 1u << (x & 31);
-            if (!(ROI[wi] & bit)) continue;
+            if (!((roi3[rr] >> cc) & 1u)) continue;
             const unsigned gv = gray[y * g.gp + x];
             if (gv < u1 || gv > u4) {
                 atomicOr(&CAND[wi], bit);
