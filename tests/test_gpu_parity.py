@@ -430,8 +430,10 @@ def test_ragged_grid_and_unaligned_frames(insp):
     cv2 oracle unit by unit."""
     import torch
     boxes = [((7, 5, 316, 315), 0), ((340, 9, 200, 150), 1), ((560, 20, 96, 96), 2), ((700, 3, 40, 33), 3),
-             ((760, 50, 13, 21), 4), ((340, 170, 333, 120), 5), ((800, 100, 150, 230), 6), ((690, 60, 3, 3), 7)]
-    W, H = 1001, 345
+             ((760, 50, 13, 21), 4), ((340, 170, 333, 120), 5), ((800, 100, 150, 230), 6), ((690, 60, 3, 3), 7),
+             ((10, 335, 500, 60), 8),        # wider than the lattice pass covers: exact rank counts for every ROI pixel
+             ((520, 340, 400, 52), 9)]       # the 15-columns-per-lane instantiation of the prefix pass
+    W, H = 1001, 400
     frames = np.stack([synth.make_frame(s, [b for b, _ in boxes], H=H, W=W, inset=6, jitter=2) for s in (11, 12)])
     excl = [{'shape': 'rect', 'x': 20, 'y': 10, 'w': 30, 'h': 12}, {'shape': 'circle', 'cx': 60, 'cy': 50, 'r': 9}]
     for params in (dict(), dict(erode_px=2, threshold=10, min_area=3)):
