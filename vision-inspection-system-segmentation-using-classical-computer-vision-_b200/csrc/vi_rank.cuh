@@ -427,9 +427,16 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, int thr, 
                     p += gp;
                 }
             } else {
-                for (int dy = -10; dy <= 10; ++dy) {
-                    const uint8_t* row = gray + min(max(y + dy, 0), hm1) * gp;
-                    for (int dx = -10; dx <= 10; ++dx) { const int v = row[min(max(x + dx, 0), wm1)]; ca += v <= pa; cb += v <= pb; }
+                // window clipped to the crop; the replicated border rows / columns enter as weights of the edge ones
+                const int xa = max(x - 10, 0), xb = min(x + 10, wm1), ya = max(y - 10, 0), yb = min(y + 10, hm1);
+                const int nl = xa - (x - 10), nr = (x + 10) - xb, mt = ya - (y - 10), mb = (y + 10) - yb;
+                for (int r = ya; r <= yb; ++r) {
+                    const uint8_t* row = gray + r * gp;
+                    const int e0 = row[0], e1 = row[wm1];
+                    int ra = nl * (e0 <= pa) + nr * (e1 <= pa), rb = nl * (e0 <= pb) + nr * (e1 <= pb);
+                    for (int c = xa; c <= xb; ++c) { const int v = row[c]; ra += v <= pa; rb += v <= pb; }
+                    const int wr = 1 + (r == 0 ? mt : 0) + (r == hm1 ? mb : 0);
+                    ca += wr * ra; cb += wr * rb;
                 }
             }
             if (ca <= 220 || cb >= 221) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
