@@ -390,6 +390,26 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
     cta_sync();
 }
 
+// Four bytes against one pivot p at a time: flag (bit 0 of each byte) = byte > p.  K and sel encode p once per
+// pixel: p < 0 -> every byte is greater; p >= 255 -> none; else the low seven bits are compared by an add that
+// carries into bit 7 and the high bit decides the rest.
+struct SwarPivot { unsigned K, sel; };
+__device__ __forceinline__ SwarPivot swar_pivot(int p) {
+    SwarPivot q;
+    if (p < 0) { q.K = 0x80808080u; q.sel = 0xffffffffu; }
+    else {
+        const int pc = min(p, 255);
+        q.K = (unsigned)(0x7f - (pc & 127)) * 0x01010101u;
+        q.sel = pc < 128 ? 0xffffffffu : 0u;
+    }
+    return q;
+}
+__device__ __forceinline__ unsigned swar_gt(unsigned W, const SwarPivot& q) {
+    const unsigned t = (W & 0x7f7f7f7fu) + q.K;              // bit 7: low seven bits > (p & 127)
+    const unsigned gt = (t & W) | ((t | W) & q.sel);          // p >= 128: high bit and low bits greater; p < 128: either
+    return (gt >> 7) & 0x01010101u;
+}
+
 // Part 2 (needs the ROI): CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
 // Returns the number of pixels that needed an exact rank count.
 template <class PT>
@@ -420,12 +440,29 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, int thr, 
             const int pa = gv + thr, pb = gv - thr - 1;
             int ca = 0, cb = 0;
             if (x >= 10 && x + 10 <= wm1 && y >= 10 && y + 10 <= hm1) {
-                const uint8_t* p = gray + (y - 10) * gp + (x - 10);
+                // window inside the crop: six aligned words per row (the crop pitch is a multiple of 4, so the byte
+                // phase o is the same on every row), bytes compared four at a time; the per-byte "greater" flags are
+                // summed as byte counters (at most 126 per lane) and the counts are 441 minus their totals.
+                const int a0 = (y - 10) * gp + (x - 10);
+                const int o = a0 & 3;
+                const unsigned* wp = reinterpret_cast<const unsigned*>(gray + (a0 - o));
+                const unsigned fm = 0x01010101u << (8 * o), lm = 0x01010101u >> (8 * (3 - o));      // first / last word bytes
+                const SwarPivot qa = swar_pivot(pa), qb = swar_pivot(pb);
+                unsigned ga = 0, gb = 0;
+                const int wpitch = gp >> 2;
                 for (int dy = 0; dy < 21; ++dy) {
 #pragma unroll
-                    for (int dx = 0; dx < 21; ++dx) { const int v = p[dx]; ca += v <= pa; cb += v <= pb; }
-                    p += gp;
+                    for (int k = 0; k < 6; ++k) {
+                        const unsigned W = wp[k];
+                        const unsigned m = k == 0 ? fm : (k == 5 ? lm : 0x01010101u);
+                        ga += swar_gt(W, qa) & m;
+                        gb += swar_gt(W, qb) & m;
+                    }
+                    wp += wpitch;
                 }
+                const unsigned sa = (ga & 0x00ff00ffu) + ((ga >> 8) & 0x00ff00ffu), sb = (gb & 0x00ff00ffu) + ((gb >> 8) & 0x00ff00ffu);
+                ca = 441 - (int)((sa & 0xffffu) + (sa >> 16));         // (the four lanes can add up to 441: no byte-wide total)
+                cb = 441 - (int)((sb & 0xffffu) + (sb >> 16));
             } else {
                 // window clipped to the crop; the replicated border rows / columns enter as weights of the edge ones
                 const int xa = max(x - 10, 0), xb = min(x + 10, wm1), ya = max(y - 10, 0), yb = min(y + 10, hm1);
