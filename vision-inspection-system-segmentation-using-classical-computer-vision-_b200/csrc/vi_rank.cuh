@@ -316,7 +316,9 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
     const int hm1 = g.h - 1;
     // V: the first 3*cpw lanes of warp v own columns 3*cpw*v .. (cpw whole cells); columns past the
     // crop edge re-read the edge column (duplicates never change a cell's min / max)
-    const int cpw = kColsPerWarp / kCell;                    // cells per warp: full warps (the pass is issue / smem-pipe bound)
+    // cells per warp: full warps for wide units (the pass is issue bound there); narrow units spread their few
+    // columns over all warps instead (latency bound: 96 columns on 4 warps left 12 idle)
+    const int cpw = nlx > 64 ? kColsPerWarp / kCell : max((nlx + kWarps - 1) / kWarps, 1);
     const int vcol = warp * cpw * kCell + lane;
     const bool vact = lane < cpw * kCell && vcol < g.w;
     const bool vwarp = warp * cpw * kCell < g.w;               // warps without a column skip the pass
