@@ -445,6 +445,28 @@ VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsign
     return const_cast<unsigned*>(cur);
 }
 
+// Four bytes against one pivot p at a time: flag (bit 0 of each byte) = byte > p.  K and sel encode p once per
+// pixel: p < 0 -> every byte is greater; p >= 255 -> none; else the low seven bits are compared by an add that
+// carries into bit 7 and the high bit decides the rest.
+struct SwarPivot { unsigned K, sel; };
+__device__ __forceinline__ SwarPivot swar_pivot(int p) {
+    SwarPivot q;
+    if (p < 0) { q.K = 0x80808080u; q.sel = 0xffffffffu; }
+    else {
+        const int pc = min(p, 255);
+        q.K = (unsigned)(0x7f - (pc & 127)) * 0x01010101u;
+        q.sel = pc < 128 ? 0xffffffffu : 0u;
+    }
+    return q;
+}
+__device__ __forceinline__ unsigned swar_gt7(unsigned W, const SwarPivot& q) {      // flags at bit 7 of each byte
+    const unsigned t = (W & 0x7f7f7f7fu) + q.K;              // bit 7: low seven bits > (p & 127)
+    return ((t & W) | ((t | W) & q.sel)) & 0x80808080u;       // p >= 128: high bit and low bits greater; p < 128: either
+}
+__device__ __forceinline__ unsigned swar_gt(unsigned W, const SwarPivot& q) { return swar_gt7(W, q) >> 7; }
+// The four bit-7 flags of a word as a nibble (bit k = byte k): one multiply lines them up at bits 28..31.
+__device__ __forceinline__ unsigned swar_nibble(unsigned f7) { return (f7 * 0x00204081u) >> 28; }
+
 __device__ inline unsigned cta_popcount(CtaScratch& cs, const unsigned* M, const Geom& g) {
     unsigned long long n = 0;
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) n += __popc(M[i]);

@@ -392,26 +392,6 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
     cta_sync();
 }
 
-// Four bytes against one pivot p at a time: flag (bit 0 of each byte) = byte > p.  K and sel encode p once per
-// pixel: p < 0 -> every byte is greater; p >= 255 -> none; else the low seven bits are compared by an add that
-// carries into bit 7 and the high bit decides the rest.
-struct SwarPivot { unsigned K, sel; };
-__device__ __forceinline__ SwarPivot swar_pivot(int p) {
-    SwarPivot q;
-    if (p < 0) { q.K = 0x80808080u; q.sel = 0xffffffffu; }
-    else {
-        const int pc = min(p, 255);
-        q.K = (unsigned)(0x7f - (pc & 127)) * 0x01010101u;
-        q.sel = pc < 128 ? 0xffffffffu : 0u;
-    }
-    return q;
-}
-__device__ __forceinline__ unsigned swar_gt(unsigned W, const SwarPivot& q) {
-    const unsigned t = (W & 0x7f7f7f7fu) + q.K;              // bit 7: low seven bits > (p & 127)
-    const unsigned gt = (t & W) | ((t | W) & q.sel);          // p >= 128: high bit and low bits greater; p < 128: either
-    return (gt >> 7) & 0x01010101u;
-}
-
 // Part 2 (needs the ROI): CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
 // Returns the number of pixels that needed an exact rank count.
 template <class PT>
