@@ -491,6 +491,40 @@ def test_seg_stats_output_matches_mask_stats(insp, golden, tmp_path):
     assert (stats == -7).all()
 
 
+def test_randomized_parameters_against_oracle(insp):
+    """Seeded sweep over the widget ranges (threshold, erosion radius, min-area, blur and morphology sizes, both
+    segmentation and defect methods) on frames of varying contrast, noise and plate geometry: every unit's masks and
+    record against the cv2 oracle."""
+    import torch
+    rng = np.random.default_rng(2024)
+    boxes = [((5, 4, 150, 141), 0), ((170, 9, 97, 120), 1), ((280, 2, 64, 64), 2), ((360, 6, 201, 150), 3)]
+    W, H = 576, 160
+    for trial in range(36):
+        params = dict(threshold=int(rng.integers(0, 70)), erode_px=int(rng.integers(0, 24)), min_area=int(rng.integers(0, 60)),
+                      gaussian_blur=int(rng.choice([0, 3, 3, 5, 6])), morph_kernel=int(rng.choice([0, 3, 3, 5, 7])))
+        if trial % 6 == 4:
+            params['defect_method'] = 'canny'
+        if trial % 9 == 7:
+            params.update(seg_method='adaptive', adapt_block=int(rng.choice([11, 31, 51])), adapt_C=int(rng.integers(2, 15)))
+        fr = synth.make_frame(1000 + trial, [b for b, _ in boxes], H=H, W=W, inset=int(rng.integers(4, 20)), jitter=2,
+                              max_discs=int(rng.integers(0, 6)), salt_p=float(rng.choice([0.0, 0.0, 0.01, 0.05])))
+        if trial % 5 == 3:                                   # low contrast: classes close together
+            fr = (fr.astype(np.int32) // 3 + 80).astype(np.uint8)
+        rp = R.Params(**{k: (v if not isinstance(v, str) else v) for k, v in params.items()})
+        recs, osegs, odefs = R.inspect_frame(fr, boxes, rp, (), None, True)
+        insp.configure(Grid(boxes=boxes), is_reference=True)
+        rec, seg, dfm = insp.inspect_batch(torch.from_numpy(fr[None]).cuda(), vi_b200.default_params(**params))
+        torch.cuda.synchronize()
+        rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+        segs = insp.split_masks(seg.cpu().numpy()); defs = insp.split_masks(dfm.cpu().numpy())
+        for u, o in enumerate(recs):
+            assert np.array_equal(segs[u], osegs[u]), (trial, params, u, 'seg', int((segs[u] != osegs[u]).sum()))
+            ref = odefs[u] if odefs[u] is not None else np.zeros_like(defs[u])
+            assert np.array_equal(defs[u], ref), (trial, params, u, 'defect', int((defs[u] != ref).sum()))
+            for k in ('seg_area', 'roi_area', 'defect_area', 'n_kept', 'status'):
+                assert rec[u][k] == o[k], (trial, params, u, k, rec[u][k], o[k])
+
+
 def test_frame_ingest(insp):
     """Device ingest against the reference's host calls: aligned frames (vector kernels) and odd
     shapes / pitches (scalar kernels), batch of frames, mono identity."""
