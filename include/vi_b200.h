@@ -17,6 +17,15 @@
  * Threading: one vi_ctx per host thread and device.  vi_inspect_batch is
  * asynchronous with respect to `stream`; all *_host / compat entry points
  * block until their results are in the caller's host buffers.
+ *
+ * Ordering: a context's tables (grid, exclusions, reference centroids) and its
+ * per-SM scratch are shared by all of its calls.  The library orders them
+ * itself: every entry point waits (on the device for a stream launch, on the host
+ * for a table update or a blocking call) for the last asynchronous
+ * vi_inspect_batch of the same context before touching them, whatever stream that
+ * batch ran on.  Output buffers of an asynchronous batch stay the caller's to
+ * synchronise.  Every entry point leaves the caller's current CUDA device as it
+ * found it.
  */
 #ifndef VI_B200_H
 #define VI_B200_H
@@ -31,7 +40,7 @@ extern "C" {
 #define VI_ERR_ARG (-1)         /* bad argument (null pointer, rect outside frame, bad size) */
 #define VI_ERR_CUDA (-2)        /* CUDA runtime / launch failure                              */
 #define VI_ERR_UNSUPPORTED (-3) /* a value the reference itself never uses (e.g. median_ksize != 21) */
-#define VI_ERR_TOO_LARGE (-4)   /* unit does not fit the shared-memory-resident path          */
+#define VI_ERR_TOO_LARGE (-4)   /* unit larger than the documented bound  */
 
 /* vi_unit_record.status */
 #define VI_STATUS_OK 0        /* detector returned None or area < min_area (indexing_ui.py:1687, :1699) */
@@ -120,16 +129,54 @@ int vi_inspect_batch(vi_ctx* ctx, const uint8_t* d_frames, int n_images, int W, 
  * does).  d_stats: device, int64 [n_images*n_units][3]; NULL switches it off. */
 int vi_set_seg_stats_output(vi_ctx* ctx, int64_t* d_stats);
 
-/* Same, from and to HOST buffers (pinned memory recommended): uploads frames in
- * chunks, overlaps copy and compute on internal streams, downloads masks and
- * records; blocks until done.  h_seg_masks / h_defect_masks may be NULL to skip
+/* Same, from and to HOST buffers: works through the batch in chunks on internal
+ * streams so that upload, compute and download overlap; blocks until done.  With
+ * VI_HOST_UPLOAD=mapped in the environment, pinned frames (cudaHostAlloc /
+ * cudaHostRegister, e.g. torch pin_memory) are not copied: the kernel gathers the
+ * unit crops from them in place over the host link.  h_seg_masks / h_defect_masks may be NULL to skip
  * that download.  This is the end-to-end call bench.py times as `e2e`. */
 int vi_inspect_batch_host(vi_ctx* ctx, const uint8_t* h_frames, int n_images, int W, int H,
                           int64_t row_pitch, int64_t image_stride, const vi_params* params,
                           uint8_t* h_seg_masks, uint8_t* h_defect_masks, vi_unit_record* h_records);
 
-/* Bytes vi_inspect_batch_host uploads for n_images frames: only the frame rows that some
- * unit covers are copied (one strided copy per merged row interval). */
+/* mask_format of vi_inspect_batch_host_fmt */
+#define VI_MASKS_BYTES 0  /* 0/255 bytes, vi_unit_pixels per image: what ROLE_BASE+1 / +2 pixmaps hold (indexing_ui.py:2355, :1608) */
+#define VI_MASKS_PACKED 1 /* 1 bit per pixel, rows of ceil(w/32) 32-bit words, first pixel = most significant bit of its
+                           * byte: the scanline layout of a 1-bit PNG (export_masks_and_csv, indexing_ui.py:2703-2730) and of
+                           * numpy.unpackbits; vi_packed_mask_bytes per image, unit u at vi_packed_mask_offsets[u]          */
+#define VI_MASKS_NONE 2   /* records only -- all run_inspection keeps (indexing_ui.py:1686-1706); mask pointers ignored   */
+
+/* vi_inspect_batch_host with a choice of mask format (VI_MASKS_BYTES = vi_inspect_batch_host itself). */
+int vi_inspect_batch_host_fmt(vi_ctx* ctx, const uint8_t* h_frames, int n_images, int W, int H,
+                              int64_t row_pitch, int64_t image_stride, const vi_params* params,
+                              int mask_format, void* h_seg_masks, void* h_defect_masks,
+                              vi_unit_record* h_records);
+
+/* Packed-bit masks (VI_MASKS_PACKED layout) as an optional extra output of subsequent vi_inspect_batch calls:
+ * device pointers, vi_packed_mask_bytes per image; NULL switches one off. */
+int vi_set_packed_mask_output(vi_ctx* ctx, uint32_t* d_seg_bits, uint32_t* d_defect_bits);
+int64_t vi_packed_mask_bytes(vi_ctx* ctx);
+int vi_packed_mask_offsets(vi_ctx* ctx, int64_t* out_byte_offsets /* n_units + 1 */);
+
+/* ---- multi-GPU: the per-unit verdict table ------------------------------------------------
+ * One process per GPU; images are sharded round robin (rank r owns global images r, r + world, ...).  The only
+ * exchange of the path is the table of 64-byte records.  It is fused into the kernel: every rank allocates a table
+ * for ALL global images (vi_peer_table_create: cudaMalloc + a CUDA IPC handle), the ranks swap handles through
+ * their launcher (torch.distributed in vi_b200.dist), map each other's tables (vi_peer_table_open) and hand the list
+ * to vi_set_record_peers.  From then on vi_inspect_batch stores every record -- with the global image index
+ * image_mul * k + image_add for local image k -- at [image * n_units + unit] of every table over NVLink, next to
+ * d_records; no collective runs on the data path.  A table is complete once all ranks' batches have finished
+ * (their streams synchronised and a barrier passed).  n = 0 switches the exchange off. */
+int vi_peer_table_create(vi_ctx* ctx, int64_t n_records, void** d_table, uint8_t* handle64 /* 64 bytes out */);
+int vi_peer_table_open(vi_ctx* ctx, const uint8_t* handle64, void** d_peer_table);
+int vi_peer_table_close(vi_ctx* ctx, void* d_peer_table);
+int vi_peer_table_destroy(vi_ctx* ctx, void* d_table);
+int vi_peer_table_read(vi_ctx* ctx, const void* d_table, int64_t n_records, vi_unit_record* h_out);   /* blocking download */
+int vi_set_record_peers(vi_ctx* ctx, void* const* d_tables, int n, int image_mul, int image_add);
+
+/* Bytes vi_inspect_batch_host moves host -> device for n_images frames.  Pageable frames: only the frame rows that
+ * some unit covers are copied (one strided copy per merged row interval) -- pass their row_pitch.  With
+ * VI_HOST_UPLOAD=mapped, pinned frames are read in place by the crop gather, unit pixels only -- pass row_pitch = 0. */
 int64_t vi_host_upload_bytes(vi_ctx* ctx, int n_images, int64_t row_pitch);
 
 /* ---- frame ingest (device pointers, asynchronous on `stream`) ---------------- */
@@ -172,7 +219,7 @@ int vi_detect_defects(vi_ctx* ctx, const uint8_t* gray, const uint8_t* seg_mask,
 
 /* ---- diagnostics -------------------------------------------------------------- */
 /* Per-phase SM cycle counts of every unit of subsequent vi_inspect_batch calls:
- * d_cycles is device memory, [n_images*n_units][32] int64 (NULL switches it off). */
+ * d_cycles is device memory, [n_images*n_units][40] int64 (NULL switches it off). */
 int vi_debug_set_profile(vi_ctx* ctx, long long* d_cycles);
 /* Compares the reciprocal-based division of the Otsu recurrence with the IEEE divide on
  * n_samples pseudo-random operand pairs; *mismatches must come back 0. */

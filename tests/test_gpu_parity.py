@@ -369,6 +369,178 @@ def test_host_batch_equals_device_batch(insp, golden):
             assert rec_h[fi * 48 + i]['status'] == recs[i]['status']
 
 
+def _records_equal(a, b):
+    for k in vi_b200.RECORD_DTYPE.names:
+        x, y = a[k], b[k]
+        ok = np.array_equal(x, y) or (x.dtype.kind == 'f' and np.array_equal(np.isnan(x), np.isnan(y)) and
+                                      np.array_equal(x[~np.isnan(x)], y[~np.isnan(y)]))
+        assert ok, k
+
+
+@pytest.mark.parametrize("chunk", ["1", "2"])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_batch_multi_chunk(insp, golden, monkeypatch, chunk, pinned):
+    """The chunked pipeline of the host-buffer call: slot wrap-around (5 images, 1 or 2 per chunk, 3 slots), the
+    chunk-local -> batch-global image index, exclusions and centroid shifts, pinned (read in place by the crop gather)
+    and pageable (staged) frames -- every record field and both mask sets against the device-resident call."""
+    import torch
+    g = golden('config4')
+    meta = g.meta
+    excl = meta['exclusions']
+    refc = {i: (float(c[0]), float(c[1])) for i, c in enumerate(g.z['ref_centroids']) if not np.isnan(c[0])}
+    insp.configure(Grid(boxes=g.boxes, exclusions=excl, ref_centroids=refc), is_reference=False)
+    boxes = [b for b, _ in g.boxes]
+    frames = np.stack([synth.make_frame(900 + i, boxes, H=meta['H'], W=meta['W']) for i in range(5)])
+    params = vi_b200.default_params(erode_px=9)
+    rec_d, seg_d, def_d = insp.inspect_batch(torch.from_numpy(frames).cuda(), params)
+    torch.cuda.synchronize()
+    rec_d = rec_d.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    assert (rec_d['dx'] != 0).any() or (rec_d['dy'] != 0).any()
+    monkeypatch.setenv("VI_HOST_CHUNK", chunk)
+    if pinned:
+        monkeypatch.setenv("VI_HOST_UPLOAD", "mapped")
+        ht = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)
+        ht.numpy()[...] = frames
+        hf = ht.numpy()
+    else:
+        hf = frames
+    rec_h, seg_h, def_h = insp.inspect_batch_host(hf, params)
+    assert np.array_equal(seg_h, seg_d.cpu().numpy()) and np.array_equal(def_h, def_d.cpu().numpy())
+    _records_equal(rec_h, rec_d)
+    n_units = len(boxes)
+    assert list(rec_h['image']) == [i for i in range(5) for _ in range(n_units)]
+    # packed-bit masks and the records-only call carry the same information
+    rec_p, seg_p, def_p = insp.inspect_batch_host(hf, params, mask_format="packed")
+    _records_equal(rec_p, rec_d)
+    for fi in range(5):
+        for a, b in zip(insp.unpack_masks(seg_p, fi), insp.split_masks(seg_h, fi)):
+            assert np.array_equal(a, b)
+        for a, b in zip(insp.unpack_masks(def_p, fi), insp.split_masks(def_h, fi)):
+            assert np.array_equal(a, b)
+    rec_n, seg_n, def_n = insp.inspect_batch_host(hf, params, mask_format="none")
+    assert seg_n is None and def_n is None
+    _records_equal(rec_n, rec_d)
+
+
+def test_packed_mask_output_of_the_device_call(insp, golden):
+    import torch
+    g = golden('config1')
+    insp.configure(Grid(boxes=g.boxes), is_reference=True)
+    d = torch.from_numpy(np.stack([g.frame(0), g.frame(0)[::-1].copy()])).cuda()
+    sb = torch.zeros(2 * insp.packed_bytes, dtype=torch.uint8, device="cuda")
+    db = torch.zeros(2 * insp.packed_bytes, dtype=torch.uint8, device="cuda")
+    rec, seg, dfm = insp.inspect_batch(d, seg_bits=sb, defect_bits=db)
+    torch.cuda.synchronize()
+    seg, dfm, sb, db = seg.cpu().numpy(), dfm.cpu().numpy(), sb.cpu().numpy(), db.cpu().numpy()
+    for fi in range(2):
+        for a, b in zip(insp.unpack_masks(sb, fi), insp.split_masks(seg, fi)):
+            assert np.array_equal(a, b)
+        for a, b in zip(insp.unpack_masks(db, fi), insp.split_masks(dfm, fi)):
+            assert np.array_equal(a, b)
+    # a later call without the packed outputs must not write them
+    sb2 = torch.from_numpy(sb.copy()).cuda()
+    insp.inspect_batch(d)
+    torch.cuda.synchronize()
+    assert np.array_equal(sb2.cpu().numpy(), sb)
+
+
+def test_calls_are_ordered_without_caller_synchronisation(insp, golden):
+    """An asynchronous batch followed at once by table updates and blocking per-unit calls of the same context (they run
+    on internal streams and share its scratch): the library orders them itself (include/vi_b200.h, Ordering)."""
+    import torch
+    g = golden('config1')
+    boxes = [b for b, _ in g.boxes]
+    frames = np.stack([synth.make_frame(700 + i, boxes) for i in range(16)])
+    d = torch.from_numpy(frames).cuda()
+    crop = crops(1)[0]
+    want_seg = R.segment_cell(crop)
+    insp.configure(Grid(boxes=g.boxes), is_reference=True)
+    ref_rec, ref_seg, ref_def = insp.inspect_batch(d)
+    torch.cuda.synchronize()
+    ref_rec, ref_seg, ref_def = ref_rec.clone(), ref_seg.clone(), ref_def.clone()
+    side = torch.cuda.Stream()
+    for rep in range(6):
+        rec, seg, dfm = insp.inspect_batch(d)                         # asynchronous, torch's current stream
+        got = insp.segment_cell(crop)                                 # internal stream, same scratch slot
+        assert np.array_equal(got, want_seg)
+        if rep % 2:
+            insp.set_grid([b for b in boxes])                         # same tables, rewritten while the batch may run
+            with torch.cuda.stream(side):
+                rec2, seg2, dfm2 = insp.inspect_batch(d)              # a second stream: ordered after the first
+            side.synchronize()
+            assert torch.equal(seg2, ref_seg) and torch.equal(rec2, ref_rec)
+        torch.cuda.synchronize()
+        assert torch.equal(seg, ref_seg) and torch.equal(dfm, ref_def) and torch.equal(rec, ref_rec)
+
+
+LARGE_UNITS = [(340, 340), (640, 480), (1000, 60), (2048, 1500)]
+
+
+@pytest.mark.parametrize("wh", LARGE_UNITS)
+def test_units_beyond_one_sm(insp, wh):
+    """Units that do not fit one SM's shared memory run the same phases over a per-CTA arena in global memory
+    (DESIGN.md section 2): segment_cell, detect_defects and the batch call, bit-exact against the oracle."""
+    import torch
+    w, h = wh
+    Wf, Hf = ((w + 48 + 15) // 16) * 16, h + 40
+    box = (19, 17, w, h)
+    inset = max(4, min(24, h // 5))
+    fr = synth.make_frame(4000 + w, [box], H=Hf, W=Wf, inset=inset, max_discs=3)
+    rng = np.random.default_rng(w)
+    for _ in range(6):                                     # more foreign material than the generator's three discs
+        cy, cx, r = int(rng.integers(17 + inset + 8, 17 + h - inset - 8)), int(rng.integers(19 + inset + 8, 19 + w - inset - 8)), int(rng.integers(2, 7))
+        yy, xx = np.ogrid[cy - r:cy + r + 1, cx - r:cx + r + 1]
+        fr[cy - r:cy + r + 1, cx - r:cx + r + 1][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = int(rng.integers(140, 255))
+    crop = fr[17:17 + h, 19:19 + w].copy()
+    want_seg = R.segment_cell(crop)
+    got_seg, t = insp.segment_cell(crop, return_threshold=True)
+    assert t == R.otsu_threshold(cv2.GaussianBlur(crop, (3, 3), 0))
+    assert np.array_equal(got_seg, want_seg), int((got_seg != want_seg).sum())
+    assert np.array_equal(insp.fill_internal_holes(want_seg), R.fill_internal_holes(want_seg))
+    a, sx, sy = insp.mask_sums(want_seg)
+    ys, xs = np.nonzero(want_seg)
+    assert (a, sx, sy) == (len(xs), int(xs.sum()), int(ys.sum()))
+    for r_, thr, mn in ((6, 24, 20), (2, 12, 0)):
+        info = {}
+        ref = R.detect_defects(crop, want_seg, 'threshold', thr, mn, r_, info)
+        got, rec = insp.detect_defects(crop, want_seg, vi_b200.default_params(threshold=thr, min_area=mn, erode_px=r_), return_record=True)
+        assert (ref is None) == (got is None)
+        if ref is not None:
+            assert np.array_equal(got, ref), int((got != ref).sum())
+            assert rec["n_kept"] == info["n_kept"] and rec["defect_area"] == int((ref > 0).sum())
+        assert rec["roi_area"] == int((info['roi'] > 0).sum())
+    # the batch call: two frames, exclusions, centroid shift against the first frame's centroids
+    excl = [{'shape': 'rect', 'x': w // 4, 'y': h // 3, 'w': w // 8, 'h': max(3, h // 10)},
+            {'shape': 'circle', 'cx': (2 * w) // 3, 'cy': h // 2, 'r': max(3, min(w, h) // 8)}]
+    fr2 = np.roll(fr, (2, -3), axis=(0, 1))
+    frames = np.stack([fr, fr2])
+    recs0, segs0, defs0 = R.inspect_frame(fr, [(box, 0)], R.Params(), excl, None, True)
+    refc = {0: (recs0[0]['cx'], recs0[0]['cy'])}
+    insp.configure(Grid(boxes=[(box, 0)], exclusions=excl, ref_centroids=refc), is_reference=False)
+    rec, seg, dfm = insp.inspect_batch(torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    seg, dfm = seg.cpu().numpy(), dfm.cpu().numpy()
+    for fi in range(2):
+        recs, segs, defs = R.inspect_frame(frames[fi], [(box, 0)], R.Params(), excl, refc, False)
+        assert np.array_equal(insp.split_masks(seg, fi)[0], segs[0])
+        d = defs[0] if defs[0] is not None else np.zeros((h, w), np.uint8)
+        assert np.array_equal(insp.split_masks(dfm, fi)[0], d)
+        for k in ('status', 'defect_area', 'seg_area', 'roi_area', 'dx', 'dy', 'n_kept'):
+            assert rec[fi][k] == recs[0][k], (fi, k, rec[fi][k], recs[0][k])
+    assert (rec[1]['dx'], rec[1]['dy']) != (0, 0)
+
+
+def test_unit_size_bound_is_documented_and_loud(insp):
+    """Beyond the documented bound (4096 wide, 8192 high, 2^24 pixels) the call fails with VI_ERR_TOO_LARGE -- no fallback."""
+    with pytest.raises(vi_b200.ViError) as e:
+        insp.set_grid([(0, 0, 5000, 100)])
+    assert e.value.code == -4
+    with pytest.raises(vi_b200.ViError) as e:
+        insp.set_grid([(0, 0, 4096, 4097)])
+    assert e.value.code == -4 and "bound" in str(e.value)
+
+
 def test_full_size_batch_properties(insp, golden):
     """BASELINE configs[1] at its full size (64 frames of 4096x3000, 3,072 units) through size-independent
     properties: the golden frame's units match the reference's outputs wherever the frame sits in the batch; copies of
@@ -568,8 +740,9 @@ def test_error_paths(insp):
         insp.segment_cell(np.zeros((8, 8), np.uint8), vi_b200.default_params(seg_method=7))             # not a reference option
     with pytest.raises(vi_b200.ViError):
         insp.segment_cell(np.zeros((8, 8), np.uint8), vi_b200.default_params(median_ksize=5))           # the reference hard-codes 21
+    insp.set_grid([(0, 0, 2000, 2000)])                                      # beyond one SM's shared memory: the arena path takes it
     with pytest.raises(vi_b200.ViError):
-        insp.set_grid([(0, 0, 2000, 2000)])                                  # does not fit shared memory
+        insp.set_grid([(0, 0, 4097, 100)])                                   # beyond the documented bound of a unit
     insp.set_grid([(10, 10, 50, 50)])
     import torch
     with pytest.raises(vi_b200.ViError):

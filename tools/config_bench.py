@@ -37,7 +37,7 @@ def config5():
     rec = out['r'][0].cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
     n = len(boxes)
     from vi_b200 import _lib
-    prof = torch.zeros((n, 32), dtype=torch.int64, device="cuda")
+    prof = torch.zeros((n, 40), dtype=torch.int64, device="cuda")
     _lib.check(insp._lib.vi_debug_set_profile(insp._ctx, prof.data_ptr()))
     insp.inspect_batch(d, p); torch.cuda.synchronize()
     _lib.check(insp._lib.vi_debug_set_profile(insp._ctx, None))

@@ -22,7 +22,7 @@ def main():
     insp = vi_b200.Inspector(0)
     insp.configure(Grid(boxes=boxes), is_reference=True)
     d = torch.from_numpy(frames).cuda()
-    prof = torch.zeros((n * 48, 32), dtype=torch.int64, device="cuda")
+    prof = torch.zeros((n * 48, 40), dtype=torch.int64, device="cuda")
     insp.inspect_batch(d)
     torch.cuda.synchronize()
     _lib.check(insp._lib.vi_debug_set_profile(insp._ctx, prof.data_ptr()))
@@ -36,10 +36,10 @@ def main():
     rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
     mean = p.mean(axis=0)
     tot = mean[:len(NAMES)].sum()
-    print(f"{n} images, {n*48} units, kernel {e0.elapsed_time(e1):.3f} ms; mean cycles/unit {tot:.0f}")
+    print(f"{n} images, {n*48} units, kernel {e0.elapsed_time(e1):.3f} ms; mean cycles/unit {mean.sum():.0f} (phase slots {tot:.0f} + sub-phase slots {mean[len(NAMES):].sum():.0f})")
     for i, nm in enumerate(NAMES):
         print(f"  {i:2d} {nm:18s} {mean[i]:10.0f}  {100*mean[i]/tot:5.1f}%   max {p[:, i].max():10.0f}")
-    for i, nm in ((20, "rank: V"), (21, "rank: S+C"), (22, "rank: classify"), (23, "ccl: count+scan"), (24, "ccl: extract"), (25, "ccl: link"), (26, "ccl: jump B"), (27, "ccl: unions"), (28, "ccl: jump D"), (29, "thr: gray mask")):
+    for i, nm in ((20, "rank: V"), (21, "rank: S+C"), (22, "rank: classify"), (23, "ccl: count+scan"), (24, "ccl: extract"), (25, "ccl: link"), (26, "ccl: jump B"), (27, "ccl: unions"), (28, "ccl: jump D"), (29, "thr: gray mask"), (30, "hist: zero"), (31, "hist: blur3 loop"), (32, "gather: wait for rows")):
         print(f"  {i:2d} {nm:18s} {mean[i]:10.0f}")
     print("  gather cycles: first unit of each CTA %.0f, later units %.0f" % (p[:148, 0].mean(), p[148:, 0].mean()))
     print("  n_ambiguous mean %.1f max %d; n_runs max %d" % (rec['n_ambiguous'].mean(), rec['n_ambiguous'].max(), rec['n_runs'].max()))

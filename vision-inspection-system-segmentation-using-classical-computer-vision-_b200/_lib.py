@@ -12,6 +12,7 @@ from . import _build
 VI_OK = 0
 VI_ERR_ARG, VI_ERR_CUDA, VI_ERR_UNSUPPORTED, VI_ERR_TOO_LARGE = -1, -2, -3, -4
 STATUS_OK, STATUS_NG, STATUS_ROI_EMPTY = 0, 1, 2
+MASKS_BYTES, MASKS_PACKED, MASKS_NONE = 0, 1, 2
 
 
 class ViParams(C.Structure):
@@ -34,7 +35,9 @@ assert RECORD_DTYPE.itemsize == 64
 EXPORTS = [
     "vi_last_error", "vi_version", "vi_params_default", "vi_ctx_create", "vi_ctx_destroy", "vi_set_grid",
     "vi_set_exclusions", "vi_set_ref_centroids", "vi_unit_pixels", "vi_unit_offsets", "vi_inspect_batch",
-    "vi_inspect_batch_host", "vi_host_upload_bytes", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
+    "vi_inspect_batch_host", "vi_inspect_batch_host_fmt", "vi_set_packed_mask_output", "vi_packed_mask_bytes",
+    "vi_packed_mask_offsets", "vi_host_upload_bytes", "vi_peer_table_create", "vi_peer_table_open", "vi_peer_table_close",
+    "vi_peer_table_destroy", "vi_peer_table_read", "vi_set_record_peers", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
     "vi_label_components", "vi_detect_defects", "vi_ingest_argb32", "vi_ingest_gray16", "vi_set_seg_stats_output", "vi_debug_set_profile", "vi_debug_fastdiv_check", "vi_debug_adaptive_taps",
 ]
 
@@ -76,6 +79,17 @@ def load():
     lib.vi_host_upload_bytes.restype = i64
     lib.vi_inspect_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, P(ViParams), vp, vp, vp, vp, vp]
     lib.vi_inspect_batch_host.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, P(ViParams), vp, vp, vp]
+    lib.vi_inspect_batch_host_fmt.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, P(ViParams), C.c_int, vp, vp, vp]
+    lib.vi_set_packed_mask_output.argtypes = [vp, vp, vp]
+    lib.vi_packed_mask_bytes.argtypes = [vp]
+    lib.vi_packed_mask_bytes.restype = i64
+    lib.vi_packed_mask_offsets.argtypes = [vp, vp]
+    lib.vi_peer_table_create.argtypes = [vp, i64, P(vp), vp]
+    lib.vi_peer_table_open.argtypes = [vp, vp, P(vp)]
+    lib.vi_peer_table_close.argtypes = [vp, vp]
+    lib.vi_peer_table_destroy.argtypes = [vp, vp]
+    lib.vi_peer_table_read.argtypes = [vp, vp, i64, vp]
+    lib.vi_set_record_peers.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     lib.vi_segment_cell.argtypes = [vp, vp, C.c_int, C.c_int, P(ViParams), vp, P(i32)]
     lib.vi_fill_internal_holes.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.vi_mask_stats.argtypes = [vp, vp, C.c_int, C.c_int, P(i64), P(i64), P(i64)]
@@ -90,7 +104,8 @@ def load():
     lib.vi_ingest_gray16.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i64, i64, vp, i64, i64, vp]
     for n in EXPORTS:
         f = getattr(lib, n)
-        if n not in ("vi_last_error", "vi_params_default", "vi_ctx_destroy", "vi_unit_pixels", "vi_version", "vi_host_upload_bytes"):
+        if n not in ("vi_last_error", "vi_params_default", "vi_ctx_destroy", "vi_unit_pixels", "vi_version", "vi_host_upload_bytes",
+                     "vi_packed_mask_bytes"):
             f.restype = C.c_int
     _lib = lib
     return lib

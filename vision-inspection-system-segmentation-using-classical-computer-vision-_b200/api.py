@@ -34,6 +34,8 @@ class Inspector:
         self.unit_pixels = 0
         self.offsets = np.zeros(1, np.int64)
         self.shapes = []
+        self.packed_bytes = 0
+        self.packed_offsets = np.zeros(1, np.int64)
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
@@ -55,6 +57,9 @@ class Inspector:
         self.offsets = np.zeros(self.n_units + 1, np.int64)
         check(self._lib.vi_unit_offsets(self._ctx, self.offsets.ctypes.data))
         self.shapes = [(int(h), int(w)) for _, _, w, h in r]
+        self.packed_bytes = int(self._lib.vi_packed_mask_bytes(self._ctx))
+        self.packed_offsets = np.zeros(self.n_units + 1, np.int64)
+        check(self._lib.vi_packed_mask_offsets(self._ctx, self.packed_offsets.ctypes.data))
 
     def set_exclusions(self, exclusions):
         rows = exclusions_to_table(exclusions or [])
@@ -80,8 +85,22 @@ class Inspector:
         self.set_ref_centroids(grid.ref_centroids, is_reference)
 
     # ---- batch calls -------------------------------------------------------------
+    @staticmethod
+    def _check_out(t, name, dev, dtype, numel):
+        """A caller-supplied output tensor must be on the frames' device, contiguous, of the right type and size."""
+        if t is None:
+            return
+        if not t.is_cuda or t.device != dev:
+            raise ValueError(f"{name} must live on {dev}, got {t.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+        if t.numel() < numel:
+            raise ValueError(f"{name} holds {t.numel()} elements, the batch needs {numel}")
+
     def inspect_batch(self, frames, params=None, seg_masks=None, defect_masks=None, records=None, labels=None,
-                      stream=None, seg_stats=None):
+                      stream=None, seg_stats=None, seg_bits=None, defect_bits=None):
         """frames: CUDA uint8 tensor [n, H, W] (row stride may exceed W).  Returns
         (records, seg_masks, defect_masks) as CUDA tensors (records: uint8 [n*units, 64]);
         asynchronous on `stream` (default: torch's current stream)."""
@@ -92,7 +111,16 @@ class Inspector:
             raise ValueError("frames must be contiguous along x")
         n, H, W = frames.shape
         dev = frames.device
+        if dev.index != self.device:
+            raise ValueError(f"frames are on {dev}, this Inspector drives cuda:{self.device}")
         total = n * self.unit_pixels
+        self._check_out(seg_masks, "seg_masks", dev, torch.uint8, total)
+        self._check_out(defect_masks, "defect_masks", dev, torch.uint8, total)
+        self._check_out(records, "records", dev, torch.uint8, n * self.n_units * 64)
+        self._check_out(labels, "labels", dev, torch.int32, total)
+        self._check_out(seg_stats, "seg_stats", dev, torch.int64, n * self.n_units * 3)
+        self._check_out(seg_bits, "seg_bits", dev, torch.uint8, n * self.packed_bytes)
+        self._check_out(defect_bits, "defect_bits", dev, torch.uint8, n * self.packed_bytes)
         if seg_masks is None:
             seg_masks = torch.empty(total, dtype=torch.uint8, device=dev)
         if defect_masks is None:
@@ -103,6 +131,9 @@ class Inspector:
         p = params if params is not None else default_params()
         # seg_stats: optional CUDA int64 [n*units, 3] (area, sum x, sum y of each final seg mask: the CSV export's numbers)
         check(self._lib.vi_set_seg_stats_output(self._ctx, seg_stats.data_ptr() if seg_stats is not None else None))
+        # seg_bits / defect_bits: optional CUDA uint8 [n * packed_bytes]: the masks as 1 bit per pixel (PNG scanline order)
+        check(self._lib.vi_set_packed_mask_output(self._ctx, seg_bits.data_ptr() if seg_bits is not None else None,
+                                                  defect_bits.data_ptr() if defect_bits is not None else None))
         check(self._lib.vi_inspect_batch(
             self._ctx, frames.data_ptr(), int(n), int(W), int(H), int(frames.stride(1)),
             int(frames.stride(0)) if n > 1 else int(frames.stride(1)) * int(H),
@@ -145,26 +176,48 @@ class Inspector:
                                          C.c_void_p(st.cuda_stream)))
         return out
 
-    def inspect_batch_host(self, frames: np.ndarray, params=None, want_masks=True, out=None):
-        """frames: host uint8 [n, H, W] (numpy, ideally backed by pinned memory).
-        Returns (records structured array, seg_masks u8[n*unit_px] | None, defect_masks | None)."""
+    def inspect_batch_host(self, frames: np.ndarray, params=None, want_masks=True, out=None, mask_format="bytes"):
+        """frames: host uint8 [n, H, W] (numpy; pinned memory -- e.g. a torch pin_memory tensor's .numpy() -- is read in
+        place by the device, pageable memory is staged).  mask_format: "bytes" (0/255, the reference's masks), "packed"
+        (1 bit per pixel, see `unpack_masks`) or "none" (records only).
+        Returns (records structured array, seg_masks u8 | None, defect_masks u8 | None)."""
         frames = _u8c(frames, "frames")
         if frames.ndim != 3:
             raise ValueError("frames must be [n, H, W]")
         n, H, W = frames.shape
-        total = n * self.unit_pixels
+        fmt = {"bytes": _lib.MASKS_BYTES, "packed": _lib.MASKS_PACKED, "none": _lib.MASKS_NONE}[mask_format]
+        if not want_masks:
+            fmt = _lib.MASKS_NONE
+        per_image = {_lib.MASKS_BYTES: self.unit_pixels, _lib.MASKS_PACKED: self.packed_bytes, _lib.MASKS_NONE: 0}[fmt]
+        total = n * per_image
         if out is not None:
             rec, seg, dfm = out
+            for nm, b in (("seg", seg), ("defect", dfm)):
+                if b is not None and fmt != _lib.MASKS_NONE and (b.dtype != np.uint8 or not b.flags.c_contiguous or b.size < total):
+                    raise ValueError(f"out {nm} buffer must be contiguous uint8 with at least {total} bytes")
+            if rec.dtype != RECORD_DTYPE or not rec.flags.c_contiguous or rec.size < n * self.n_units:
+                raise ValueError("out records buffer must be a contiguous RECORD_DTYPE array of n * units entries")
         else:
             rec = np.empty(n * self.n_units, RECORD_DTYPE)
-            seg = np.empty(total, np.uint8) if want_masks else None
-            dfm = np.empty(total, np.uint8) if want_masks else None
+            seg = np.empty(total, np.uint8) if fmt != _lib.MASKS_NONE else None
+            dfm = np.empty(total, np.uint8) if fmt != _lib.MASKS_NONE else None
+        if fmt == _lib.MASKS_NONE:
+            seg = dfm = None
         p = params if params is not None else default_params()
-        check(self._lib.vi_inspect_batch_host(
-            self._ctx, frames.ctypes.data, int(n), int(W), int(H), int(W), int(H) * int(W), C.byref(p),
+        check(self._lib.vi_inspect_batch_host_fmt(
+            self._ctx, frames.ctypes.data, int(n), int(W), int(H), int(W), int(H) * int(W), C.byref(p), fmt,
             seg.ctypes.data if seg is not None else None, dfm.ctypes.data if dfm is not None else None,
             rec.ctypes.data))
         return rec, seg, dfm
+
+    def unpack_masks(self, packed, image=0):
+        """One image's packed-bit mask block (mask_format="packed") as a list of (h, w) uint8 0/255 arrays."""
+        base = image * self.packed_bytes
+        out = []
+        for u, (h, w) in enumerate(self.shapes):
+            blk = np.asarray(packed[base + self.packed_offsets[u]: base + self.packed_offsets[u + 1]]).reshape(h, -1)
+            out.append(np.unpackbits(blk, axis=1)[:, :w] * np.uint8(255))
+        return out
 
     def split_masks(self, flat, image=0):
         """View one image's packed mask block as a list of (h, w) arrays."""

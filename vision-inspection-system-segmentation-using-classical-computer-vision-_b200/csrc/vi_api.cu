@@ -34,6 +34,20 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(VI_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));  \
     } while (0)
 
+// Sets the context's device for the duration of an entry point and restores the caller's current device.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true, changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) { ok = cudaSetDevice(dev) == cudaSuccess; changed = ok; }
+    }
+    ~DeviceGuard() { if (prev >= 0 && changed) cudaSetDevice(prev); }
+};
+#define VI_DEVICE(c)                                                                               \
+    DeviceGuard dg_((c)->device);                                                                  \
+    if (!dg_.ok) return fail(VI_ERR_CUDA, "cudaSetDevice(%d) failed", (c)->device)
+
 struct DevBuf {
     void* p = nullptr;
     size_t n = 0;
@@ -56,8 +70,11 @@ struct GridState {
     std::vector<long long> off;     // n+1
     long long unit_px = 0;
     int wmax = 0, hmax = 0;
-    DevBuf d_rects, d_off;
+    std::vector<long long> woff;    // n+1: packed-bit mask offsets in 32-bit words
+    long long unit_words = 0;
+    DevBuf d_rects, d_off, d_woff;
     SmemPlan plan{};
+    bool gmem = false;              // units beyond one SM's shared memory: the global-arena kernel
 };
 
 struct vi_ctx {
@@ -73,6 +90,7 @@ struct vi_ctx {
     bool has_refc = false;
     int is_reference = 0;
     DevBuf scratch;
+    DevBuf arena;
     long long scratch_stride = 0;
     long long scratch_f32_off = 0;
     long long scratch_rank_off = 0;
@@ -83,7 +101,41 @@ struct vi_ctx {
     int smem_set = 0;
     long long* prof = nullptr;
     long long* seg_stats = nullptr;
+    uint32_t* seg_bits = nullptr;   // optional packed-bit outputs of vi_inspect_batch (vi_set_packed_mask_output)
+    uint32_t* def_bits = nullptr;
+    // Ordering: the context's tables and per-CTA scratch are shared by every call.  `busy` is recorded after each
+    // asynchronous launch on a caller's stream; every later entry point waits on it (streams: cudaStreamWaitEvent,
+    // host-side table updates: cudaEventSynchronize) before it touches them.
+    cudaEvent_t busy = nullptr;
+    bool busy_set = false;
+    // multi-GPU record exchange (vi_set_record_peers)
+    vi_unit_record* peer_rec[kMaxPeers] = {};
+    int n_peers = 0, image_mul = 1, image_add = 0;
 };
+
+static int wait_busy_host(vi_ctx* c) {
+    if (c->busy_set) {
+        cudaError_t e = cudaEventSynchronize(c->busy);
+        if (e != cudaSuccess) return fail(VI_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+        c->busy_set = false;
+    }
+    return VI_OK;
+}
+
+static int wait_busy_stream(vi_ctx* c, cudaStream_t st) {
+    if (c->busy_set) {
+        cudaError_t e = cudaStreamWaitEvent(st, c->busy, 0);
+        if (e != cudaSuccess) return fail(VI_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+    }
+    return VI_OK;
+}
+
+static int mark_busy(vi_ctx* c, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(c->busy, st);
+    if (e != cudaSuccess) return fail(VI_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+    c->busy_set = true;
+    return VI_OK;
+}
 
 extern "C" const char* vi_last_error(void) { return g_err.c_str(); }
 extern "C" int vi_version(void) { return 100; }
@@ -100,7 +152,8 @@ extern "C" int vi_ctx_create(int device, vi_ctx** out) {
     int n = 0;
     CU(cudaGetDeviceCount(&n));
     if (device < 0 || device >= n) return fail(VI_ERR_ARG, "vi_ctx_create: device %d of %d", device, n);
-    CU(cudaSetDevice(device));
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(VI_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     vi_ctx* c = new vi_ctx();
@@ -108,11 +161,15 @@ extern "C" int vi_ctx_create(int device, vi_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, vi_unit_kernel<false>));
+    CU(cudaFuncGetAttributes(&fa, vi_unit_kernel<false, false, false>));
     c->smem_static = ((int)fa.sharedSizeBytes + 15) & ~15;
     for (auto& s : c->streams) {
         cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete c; return fail(VI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    }
+    {
+        cudaError_t e = cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming);
+        if (e != cudaSuccess) { vi_ctx_destroy(c); return fail(VI_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
     }
     *out = c;
     return VI_OK;
@@ -120,10 +177,11 @@ extern "C" int vi_ctx_create(int device, vi_ctx** out) {
 
 extern "C" void vi_ctx_destroy(vi_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     cudaDeviceSynchronize();
-    for (GridState* g : {&c->grid, &c->one}) { g->d_rects.release(); g->d_off.release(); }
-    for (DevBuf* b : {&c->d_excl, &c->d_refc, &c->scratch, &c->st_in, &c->st_aux, &c->st_out, &c->st_out2, &c->st_rec,
+    if (c->busy) cudaEventDestroy(c->busy);
+    for (GridState* g : {&c->grid, &c->one}) { g->d_rects.release(); g->d_off.release(); g->d_woff.release(); }
+    for (DevBuf* b : {&c->d_excl, &c->d_refc, &c->scratch, &c->arena, &c->st_in, &c->st_aux, &c->st_out, &c->st_out2, &c->st_rec,
                       &c->st_stats, &c->st_lab})
         b->release();
     for (int i = 0; i < kHostSlots; ++i) {
@@ -140,35 +198,46 @@ static int set_grid_state(vi_ctx* c, GridState& gs, const int32_t* r, int n, cud
     if (!r || n <= 0) return fail(VI_ERR_ARG, "grid: need at least one rect");
     gs.rects.resize(n);
     gs.off.assign(n + 1, 0);
+    gs.woff.assign(n + 1, 0);
     gs.wmax = gs.hmax = 0;
     for (int i = 0; i < n; ++i) {
         int x = r[4 * i], y = r[4 * i + 1], w = r[4 * i + 2], h = r[4 * i + 3];
         if (w <= 0 || h <= 0 || x < 0 || y < 0) return fail(VI_ERR_ARG, "grid: rect %d = (%d,%d,%d,%d) is invalid", i, x, y, w, h);
-        if (w > 65535 || h > 65535) return fail(VI_ERR_TOO_LARGE, "grid: rect %d is %dx%d", i, w, h);
+        if (w > kMaxUnitW || h > kMaxUnitH) return fail(VI_ERR_TOO_LARGE, "grid: rect %d is %dx%d: beyond the bound of a unit (%d wide, %d high)", i, w, h, kMaxUnitW, kMaxUnitH);
         gs.rects[i] = make_int4(x, y, w, h);
         gs.off[i + 1] = gs.off[i] + (long long)w * h;
+        gs.woff[i + 1] = gs.woff[i] + (long long)((w + 31) / 32) * h;
         gs.wmax = std::max(gs.wmax, w);
         gs.hmax = std::max(gs.hmax, h);
     }
     gs.unit_px = gs.off[n];
+    gs.unit_words = gs.woff[n];
     int gray_need = 0, words_need = 0;
     for (int i = 0; i < n; ++i) {
         const Geom g = make_geom(gs.rects[i].z, gs.rects[i].w);
         gray_need = std::max(gray_need, g.gp * g.h);
         words_need = std::max(words_need, g.nwords);
     }
-    if (!make_plan(gs.wmax, gs.hmax, c->smem_optin, c->smem_static, &gs.plan, gray_need, words_need))
-        return fail(VI_ERR_TOO_LARGE, "grid: its largest units (up to %d wide, %d high, %d crop bytes) do not fit the %d-byte "
-                    "shared-memory-resident path", gs.wmax, gs.hmax, gray_need, c->smem_optin);
+    gs.gmem = false;
+    if (!make_plan(gs.wmax, gs.hmax, c->smem_optin, c->smem_static, &gs.plan, gray_need, words_need)) {
+        // larger than one SM's shared memory: same pipeline over a per-CTA arena in global memory
+        gs.gmem = true;
+        if (!make_plan_gmem(gs.wmax, gs.hmax, &gs.plan, gray_need, words_need))
+            return fail(VI_ERR_TOO_LARGE, "grid: units up to %d x %d exceed the bound of a unit (%d wide, %d high, %lld pixels)",
+                        gs.wmax, gs.hmax, kMaxUnitW, kMaxUnitH, kMaxUnitPixels);
+    }
     int rc;
     if ((rc = gs.d_rects.ensure(sizeof(int4) * n))) return rc;
     if ((rc = gs.d_off.ensure(sizeof(long long) * (n + 1)))) return rc;
+    if ((rc = gs.d_woff.ensure(sizeof(long long) * (n + 1)))) return rc;
     if (st) {
         CU(cudaMemcpyAsync(gs.d_rects.p, gs.rects.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(gs.d_off.p, gs.off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(gs.d_woff.p, gs.woff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
     } else {
         CU(cudaMemcpy(gs.d_rects.p, gs.rects.data(), sizeof(int4) * n, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(gs.d_off.p, gs.off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(gs.d_woff.p, gs.woff.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
         CU(cudaDeviceSynchronize());
     }
     return VI_OK;
@@ -176,7 +245,9 @@ static int set_grid_state(vi_ctx* c, GridState& gs, const int32_t* r, int n, cud
 
 extern "C" int vi_set_grid(vi_ctx* c, const int32_t* rects, int n) {
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
-    CU(cudaSetDevice(c->device));
+    VI_DEVICE(c);
+    int rcw;
+    if ((rcw = wait_busy_host(c))) return rcw;             // an in-flight batch may still be reading the tables
     c->has_refc = false;     // grid changed: reference centroids no longer valid (indexing_ui.py:2196-2200)
     return set_grid_state(c, c->grid, rects, n);
 }
@@ -185,7 +256,9 @@ extern "C" int vi_set_exclusions(vi_ctx* c, const vi_excl* e, int n) {
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
     if (n < 0 || (n > 0 && !e)) return fail(VI_ERR_ARG, "exclusions: bad arguments");
     if (n > 4096) return fail(VI_ERR_ARG, "exclusions: %d is too many", n);
-    CU(cudaSetDevice(c->device));
+    VI_DEVICE(c);
+    int rcw;
+    if ((rcw = wait_busy_host(c))) return rcw;
     c->excl.assign(e, e + n);
     if (n) {
         int rc;
@@ -198,7 +271,9 @@ extern "C" int vi_set_exclusions(vi_ctx* c, const vi_excl* e, int n) {
 
 extern "C" int vi_set_ref_centroids(vi_ctx* c, const double* cxcy, int n_units, int is_reference) {
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
-    CU(cudaSetDevice(c->device));
+    VI_DEVICE(c);
+    int rcw;
+    if ((rcw = wait_busy_host(c))) return rcw;
     c->is_reference = is_reference ? 1 : 0;
     if (!cxcy) { c->has_refc = false; return VI_OK; }
     if (n_units != (int)c->grid.rects.size()) return fail(VI_ERR_ARG, "ref centroids: %d entries for %zu units", n_units, c->grid.rects.size());
@@ -238,7 +313,7 @@ __global__ void fastdiv_check_kernel(unsigned long long seed, long long per_thre
 
 extern "C" int vi_debug_fastdiv_check(vi_ctx* c, long long n_samples, unsigned long long seed, long long* mismatches) {
     if (!c || !mismatches) return fail(VI_ERR_ARG, "vi_debug_fastdiv_check: null");
-    CU(cudaSetDevice(c->device));
+    VI_DEVICE(c);
     unsigned long long* d_bad = nullptr;
     CU(cudaMalloc(&d_bad, 8));
     CU(cudaMemset(d_bad, 0, 8));
@@ -267,6 +342,7 @@ extern "C" int vi_set_seg_stats_output(vi_ctx* c, int64_t* d_stats) {
 
 extern "C" int64_t vi_host_upload_bytes(vi_ctx* c, int n_images, int64_t row_pitch) {
     if (!c) return 0;
+    if (row_pitch <= 0) return (int64_t)c->grid.unit_px * n_images;          // mapped pinned frames: the crops only
     std::vector<std::pair<int, int>> iv;
     for (const int4& r : c->grid.rects) iv.emplace_back(r.y, r.y + r.w);
     std::sort(iv.begin(), iv.end());
@@ -278,6 +354,81 @@ extern "C" int64_t vi_host_upload_bytes(vi_ctx* c, int n_images, int64_t row_pit
         end = std::max(end, p.second);
     }
     return (int64_t)rows * row_pitch * n_images;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU: per-unit record tables in peer-mapped memory (CUDA IPC over NVLink / NVSwitch)
+// ---------------------------------------------------------------------------
+extern "C" int vi_peer_table_create(vi_ctx* c, int64_t n_records, void** d_table, uint8_t* handle64) {
+    if (!c || !d_table || !handle64 || n_records <= 0) return fail(VI_ERR_ARG, "vi_peer_table_create: bad arguments");
+    VI_DEVICE(c);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, sizeof(vi_unit_record) * (size_t)n_records));          // a whole allocation: IPC handles name allocations
+    CU(cudaMemset(p, 0, sizeof(vi_unit_record) * (size_t)n_records));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(VI_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    *d_table = p;
+    return VI_OK;
+}
+
+extern "C" int vi_peer_table_open(vi_ctx* c, const uint8_t* handle64, void** d_peer) {
+    if (!c || !handle64 || !d_peer) return fail(VI_ERR_ARG, "vi_peer_table_open: bad arguments");
+    VI_DEVICE(c);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU(cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess));
+    return VI_OK;
+}
+
+extern "C" int vi_peer_table_close(vi_ctx* c, void* d_peer) {
+    if (!c || !d_peer) return fail(VI_ERR_ARG, "vi_peer_table_close: bad arguments");
+    VI_DEVICE(c);
+    CU(cudaIpcCloseMemHandle(d_peer));
+    return VI_OK;
+}
+
+extern "C" int vi_peer_table_destroy(vi_ctx* c, void* d_table) {
+    if (!c || !d_table) return fail(VI_ERR_ARG, "vi_peer_table_destroy: bad arguments");
+    VI_DEVICE(c);
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(d_table));
+    return VI_OK;
+}
+
+extern "C" int vi_peer_table_read(vi_ctx* c, const void* d_table, int64_t n_records, vi_unit_record* h_out) {
+    if (!c || !d_table || !h_out || n_records <= 0) return fail(VI_ERR_ARG, "vi_peer_table_read: bad arguments");
+    VI_DEVICE(c);
+    CU(cudaMemcpy(h_out, d_table, sizeof(vi_unit_record) * (size_t)n_records, cudaMemcpyDeviceToHost));
+    return VI_OK;
+}
+
+extern "C" int vi_set_record_peers(vi_ctx* c, void* const* d_tables, int n, int image_mul, int image_add) {
+    if (!c) return fail(VI_ERR_ARG, "ctx is null");
+    if (n < 0 || n > kMaxPeers || (n > 0 && !d_tables)) return fail(VI_ERR_ARG, "vi_set_record_peers: %d tables (at most %d)", n, kMaxPeers);
+    if (n > 0 && (image_mul <= 0 || image_add < 0)) return fail(VI_ERR_ARG, "vi_set_record_peers: image index map %d * k + %d", image_mul, image_add);
+    for (int i = 0; i < kMaxPeers; ++i) c->peer_rec[i] = i < n ? (vi_unit_record*)d_tables[i] : nullptr;
+    c->n_peers = n;
+    c->image_mul = n > 0 ? image_mul : 1;
+    c->image_add = n > 0 ? image_add : 0;
+    return VI_OK;
+}
+
+extern "C" int vi_set_packed_mask_output(vi_ctx* c, uint32_t* d_seg_bits, uint32_t* d_def_bits) {
+    if (!c) return fail(VI_ERR_ARG, "ctx is null");
+    c->seg_bits = d_seg_bits; c->def_bits = d_def_bits;
+    return VI_OK;
+}
+
+extern "C" int64_t vi_packed_mask_bytes(vi_ctx* c) { return c ? c->grid.unit_words * 4 : 0; }
+
+extern "C" int vi_packed_mask_offsets(vi_ctx* c, int64_t* out) {
+    if (!c || !out) return fail(VI_ERR_ARG, "vi_packed_mask_offsets: null");
+    for (size_t i = 0; i < c->grid.woff.size(); ++i) out[i] = c->grid.woff[i] * 4;
+    return VI_OK;
 }
 
 extern "C" int64_t vi_unit_pixels(vi_ctx* c) { return c ? c->grid.unit_px : 0; }
@@ -398,7 +549,7 @@ static int fill_params(KArgs& a, const vi_params* p) {
     return VI_OK;
 }
 
-static int ensure_scratch(vi_ctx* c, int wmax, int hmax, int nblocks, bool f32_plane) {
+static long long scratch_layout(vi_ctx* c, int wmax, int hmax, bool f32_plane) {
     long long px = (long long)wmax * hmax;
     long long capg = (long long)hmax * (wmax / 2 + 1);
     long long px4 = (long long)((wmax + 3) & ~3) * hmax;
@@ -409,8 +560,10 @@ static int ensure_scratch(vi_ctx* c, int wmax, int hmax, int nblocks, bool f32_p
     c->scratch_f32_off = stride;
     if (f32_plane) stride += (px * 4 + 255) & ~255ll;       // float plane of the adaptive mean, only when asked for
     c->scratch_stride = stride;
-    return c->scratch.ensure((size_t)stride * nblocks);
+    return stride;
 }
+
+constexpr long long kScratchBudget = 24ll << 30;            // per-CTA scratch + arenas of the large-unit path stay below this
 
 // `slot` selects a private copy of the per-CTA scratch so launches on the internal
 // streams never share it.
@@ -418,25 +571,51 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     const long long n_total = (long long)a.n_images * a.n_units;
     if (n_total <= 0) return VI_OK;
     if (n_total > 0x7fffffffll) return fail(VI_ERR_ARG, "too many units in one call");
-    int nblocks = (int)std::min<long long>(n_total, c->sm_count);
     int rc;
-    if ((rc = ensure_scratch(c, gs.wmax, gs.hmax, kHostSlots * c->sm_count, a.p.seg_method == 1))) return rc;
-    a.scratch = (uint8_t*)c->scratch.p + (size_t)slot * c->sm_count * c->scratch_stride;
-    a.scratch_stride = c->scratch_stride;
+    const long long stride = scratch_layout(c, gs.wmax, gs.hmax, a.p.seg_method == 1);
+    const long long astride = gs.gmem ? plan_arena_bytes(gs.plan) : 0;
+    // CTAs per slot: one per SM; fewer when the units are so large that their scratch would not fit the budget
+    int bps = c->sm_count;
+    if ((stride + astride) * kHostSlots * bps > kScratchBudget)
+        bps = (int)std::max<long long>(1, kScratchBudget / ((stride + astride) * kHostSlots));
+    const int nblocks = (int)std::min<long long>(n_total, bps);
+    if ((rc = c->scratch.ensure((size_t)stride * kHostSlots * bps))) return rc;
+    if (gs.gmem && (rc = c->arena.ensure((size_t)astride * kHostSlots * bps))) return rc;
+    a.scratch = (uint8_t*)c->scratch.p + (size_t)slot * bps * stride;
+    a.scratch_stride = stride;
     a.scratch_f32_off = c->scratch_f32_off;
     a.scratch_rank_off = c->scratch_rank_off;
+    a.arena = gs.gmem ? (uint8_t*)c->arena.p + (size_t)slot * bps * astride : nullptr;
+    a.arena_stride = astride;
     a.wmax = gs.wmax; a.hmax = gs.hmax;
     a.plan = gs.plan;
     a.prof = (&gs == &c->grid) ? c->prof : nullptr;
     if (&gs != &c->grid) a.seg_stats = nullptr;
     if (c->smem_set < gs.plan.total) {
-        CU(cudaFuncSetAttribute(vi_unit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
-        CU(cudaFuncSetAttribute(vi_unit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - c->smem_static));
-        c->smem_set = c->smem_optin - c->smem_static;
+        const int lim = c->smem_optin - c->smem_static;
+        CU(cudaFuncSetAttribute(vi_unit_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CU(cudaFuncSetAttribute(vi_unit_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CU(cudaFuncSetAttribute(vi_unit_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        CU(cudaFuncSetAttribute(vi_unit_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        c->smem_set = lim;
     }
     if (gs.plan.total > c->smem_set) return fail(VI_ERR_TOO_LARGE, "shared-memory plan %d > %d", gs.plan.total, c->smem_set);
-    if (a.prof) vi_unit_kernel<true><<<nblocks, kThreads, gs.plan.total, stream>>>(a);       // diagnostics build: phase timers
-    else vi_unit_kernel<false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);
+    if (gs.gmem) {
+        // units beyond one SM's shared memory: same phases over the CTA's global arena
+        a.prof = nullptr;
+        vi_unit_kernel<false, false, true><<<nblocks, kThreads, gs.plan.total, stream>>>(a);
+        CU(cudaGetLastError());
+        return VI_OK;
+    }
+    // The default configuration has its own instantiation (vi_unit.cuh: SPEC); VI_KERNEL=general switches it off.
+    bool spec = a.mode == MODE_FULL && a.blur_k == 3 && a.se_k == 3 && a.p.seg_method == 0 && a.p.defect_method == 0 &&
+                !a.labels_out && !a.seg_stats && !a.seg_bits && !a.def_bits && !a.aux_mask && !a.stats_out &&
+                (a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0 &&
+                gs.wmax <= kRankMaxW && rank_ws_bytes(gs.wmax) + kOtsuWsBytes <= gs.plan.ws_bytes && gs.plan.n_hist >= kWarps / 2;
+    if (spec) { const char* e = getenv("VI_KERNEL"); if (e && strcmp(e, "general") == 0) spec = false; }
+    if (a.prof && spec) vi_unit_kernel<true, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);   // diagnostics build: phase timers
+    else if (spec) vi_unit_kernel<false, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);
+    else { a.prof = nullptr; vi_unit_kernel<false, false, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a); }
     CU(cudaGetLastError());
     return VI_OK;
 }
@@ -459,6 +638,9 @@ static void base_args(vi_ctx* c, KArgs& a, const GridState& gs) {
     a.n_units = (int)gs.rects.size();
     a.unit_off = (const long long*)gs.d_off.p;
     a.unit_px = gs.unit_px;
+    a.unit_woff = (const long long*)gs.d_woff.p;
+    a.unit_words = gs.unit_words;
+    a.image_mul = 1;
 }
 
 extern "C" int vi_inspect_batch(vi_ctx* c, const uint8_t* d_frames, int n_images, int W, int H, int64_t row_pitch,
@@ -467,7 +649,8 @@ extern "C" int vi_inspect_batch(vi_ctx* c, const uint8_t* d_frames, int n_images
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
     if (c->grid.rects.empty()) return fail(VI_ERR_ARG, "vi_inspect_batch: no grid set");
     if (!d_frames || !d_rec) return fail(VI_ERR_ARG, "vi_inspect_batch: frames / records pointer is null");
-    CU(cudaSetDevice(c->device));
+    if (n_images == 1 && image_stride < row_pitch * (int64_t)H) image_stride = row_pitch * (int64_t)H;
+    VI_DEVICE(c);
     int rc;
     if ((rc = check_frames(c->grid, n_images, W, H, row_pitch, image_stride))) return rc;
     KArgs a;
@@ -480,37 +663,66 @@ extern "C" int vi_inspect_batch(vi_ctx* c, const uint8_t* d_frames, int n_images
     a.seg_out = d_seg; a.def_out = d_def; a.labels_out = d_labels; a.rec = d_rec;
     a.mode = MODE_FULL;
     a.seg_stats = c->seg_stats;
-    return launch_units(c, a, c->grid, (cudaStream_t)stream);
+    a.seg_bits = c->seg_bits; a.def_bits = c->def_bits;
+    a.n_peers = c->n_peers; a.image_mul = c->image_mul; a.image_base = c->image_add;
+    for (int i = 0; i < c->n_peers; ++i) a.peer_rec[i] = c->peer_rec[i];
+    if ((rc = wait_busy_stream(c, (cudaStream_t)stream))) return rc;     // an earlier batch on another stream shares the scratch
+    if ((rc = launch_units(c, a, c->grid, (cudaStream_t)stream))) return rc;
+    return mark_busy(c, (cudaStream_t)stream);
 }
 
-extern "C" int vi_inspect_batch_host(vi_ctx* c, const uint8_t* h_frames, int n_images, int W, int H, int64_t row_pitch,
-                                     int64_t image_stride, const vi_params* params, uint8_t* h_seg, uint8_t* h_def,
-                                     vi_unit_record* h_rec) {
+// Host-buffer batch call.  mask_format: VI_MASKS_BYTES (0/255 bytes, what the reference's pixmaps hold),
+// VI_MASKS_PACKED (1 bit per pixel, rows of 32-bit words, PNG bit order) or VI_MASKS_NONE (records only: all that
+// run_inspection needs, indexing_ui.py:1686-1706).
+static int host_batch(vi_ctx* c, const uint8_t* h_frames, int n_images, int W, int H, int64_t row_pitch, int64_t image_stride,
+                      const vi_params* params, int mask_format, void* h_seg, void* h_def, vi_unit_record* h_rec) {
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
     if (c->grid.rects.empty()) return fail(VI_ERR_ARG, "vi_inspect_batch_host: no grid set");
     if (!h_frames || !h_rec) return fail(VI_ERR_ARG, "vi_inspect_batch_host: frames / records pointer is null");
-    CU(cudaSetDevice(c->device));
+    if (mask_format < VI_MASKS_BYTES || mask_format > VI_MASKS_NONE) return fail(VI_ERR_ARG, "mask_format %d", mask_format);
+    VI_DEVICE(c);
     int rc;
+    if (n_images == 1 && image_stride < row_pitch * (int64_t)H) image_stride = row_pitch * (int64_t)H;   // one frame: the stride is moot
     if ((rc = check_frames(c->grid, n_images, W, H, row_pitch, image_stride))) return rc;
+    if ((rc = wait_busy_host(c))) return rc;
+    KArgs a0;
+    base_args(c, a0, c->grid);
+    if ((rc = fill_params(a0, params))) return rc;                     // validated before anything is in flight
     const int n_units = (int)c->grid.rects.size();
     const long long upx = c->grid.unit_px;
-    // Chunks of about two units per SM, kHostSlots of them in flight.  The call is PCIe-bound (the two byte masks
-    // down, the covered frame rows up: measured ~76 GB/s aggregate over both directions, chunk sizes from 2 to 13
-    // images within 10 % of each other), so all that matters is that the copy engines never idle.
-    // VI_HOST_CHUNK overrides (images per chunk).
+    const long long ubytes = mask_format == VI_MASKS_BYTES ? upx : mask_format == VI_MASKS_PACKED ? c->grid.unit_words * 4 : 0;
+    if (mask_format == VI_MASKS_NONE) { h_seg = nullptr; h_def = nullptr; }
+    // Chunks of about two units per SM, kHostSlots of them in flight: the call is bound by the host link (frames up,
+    // masks down), so all that matters is that the copy engines never idle.  VI_HOST_CHUNK overrides (images per chunk).
     int chunk = std::max(1, (2 * c->sm_count + n_units - 1) / n_units);
     if (const char* e = getenv("VI_HOST_CHUNK")) { int v = atoi(e); if (v > 0) chunk = v; }
     chunk = std::min(chunk, n_images);
+    // Upload.  Default: one strided copy per merged row interval of the grid into a device staging buffer (the copy
+    // engine moves whole frame rows at the link rate).  VI_HOST_UPLOAD=mapped: pinned host frames that the device can
+    // address (cudaHostAlloc / cudaHostRegister under unified addressing) are not copied at all -- the crop gather of
+    // the kernel reads them in place over the host link, so only the pixels inside unit rects cross it (38.9 % of a
+    // frame for grid.json).  Measured on a B200 / PCIe Gen5 x16: the in-place gather is latency-bound per unit
+    // (16.2 ms per 64-frame step against 14.6 ms staged), so it is opt-in: it pays where the host link is shared.
+    const uint8_t* d_mapped = nullptr;
+    {
+        const char* e = getenv("VI_HOST_UPLOAD");
+        if (e && strcmp(e, "mapped") == 0) {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, h_frames) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+                d_mapped = (const uint8_t*)pa.devicePointer;
+            cudaGetLastError();                                       // an unregistered pointer may leave an error behind
+        }
+    }
     const size_t frame_bytes = (size_t)image_stride;
     for (int b = 0; b < kHostSlots; ++b) {
-        if ((rc = c->hb_frames[b].ensure(frame_bytes * chunk))) return rc;
-        if ((rc = c->hb_seg[b].ensure((size_t)upx * chunk))) return rc;
-        if ((rc = c->hb_def[b].ensure((size_t)upx * chunk))) return rc;
+        if (!d_mapped && (rc = c->hb_frames[b].ensure(frame_bytes * chunk))) return rc;
+        if (h_seg && (rc = c->hb_seg[b].ensure((size_t)ubytes * chunk))) return rc;
+        if (h_def && (rc = c->hb_def[b].ensure((size_t)ubytes * chunk))) return rc;
         if ((rc = c->hb_rec[b].ensure(sizeof(vi_unit_record) * (size_t)n_units * chunk))) return rc;
     }
     // merged [y0, y1) row intervals covered by the grid
     std::vector<std::pair<int, int>> rows;
-    {
+    if (!d_mapped) {
         std::vector<std::pair<int, int>> iv;
         for (const int4& r : c->grid.rects) iv.emplace_back(r.y, r.y + r.w);
         std::sort(iv.begin(), iv.end());
@@ -519,40 +731,59 @@ extern "C" int vi_inspect_batch_host(vi_ctx* c, const uint8_t* h_frames, int n_i
             else rows.push_back(p);
         }
     }
-    int slot = 0;
-    for (int i0 = 0; i0 < n_images; i0 += chunk, slot = (slot + 1) % kHostSlots) {
-        const int n = std::min(chunk, n_images - i0);
-        cudaStream_t st = c->streams[slot];
-        // the slot's previous chunk (kHostSlots iterations ago) is ordered before this one on the same stream
-        // upload only the frame rows some unit covers: one strided copy per merged row interval
-        for (const auto& iv : rows) {
-            const size_t off = (size_t)iv.first * row_pitch, bytes = (size_t)(iv.second - iv.first) * row_pitch;
-            CU(cudaMemcpy2DAsync((uint8_t*)c->hb_frames[slot].p + off, frame_bytes, h_frames + (size_t)i0 * image_stride + off,
-                                 (size_t)image_stride, bytes, n, cudaMemcpyHostToDevice, st));
+    auto run_chunks = [&]() -> int {
+        int slot = 0;
+        for (int i0 = 0; i0 < n_images; i0 += chunk, slot = (slot + 1) % kHostSlots) {
+            const int n = std::min(chunk, n_images - i0);
+            cudaStream_t st = c->streams[slot];
+            // the slot's previous chunk (kHostSlots iterations ago) is ordered before this one on the same stream
+            for (const auto& iv : rows) {
+                const size_t off = (size_t)iv.first * row_pitch, bytes = (size_t)(iv.second - iv.first) * row_pitch;
+                CU(cudaMemcpy2DAsync((uint8_t*)c->hb_frames[slot].p + off, frame_bytes, h_frames + (size_t)i0 * image_stride + off,
+                                     (size_t)image_stride, bytes, n, cudaMemcpyHostToDevice, st));
+            }
+            KArgs a = a0;
+            a.frames = d_mapped ? d_mapped + (size_t)i0 * image_stride : (const uint8_t*)c->hb_frames[slot].p;
+            a.n_images = n; a.W = W; a.H = H; a.row_pitch = row_pitch; a.image_stride = image_stride;
+            a.image_base = i0;
+            a.excl = (const vi_excl*)c->d_excl.p; a.n_excl = (int)c->excl.size();
+            a.refc = c->has_refc ? (const double*)c->d_refc.p : nullptr;
+            a.is_reference = c->is_reference;
+            if (mask_format == VI_MASKS_BYTES) {
+                a.seg_out = h_seg ? (uint8_t*)c->hb_seg[slot].p : nullptr; a.def_out = h_def ? (uint8_t*)c->hb_def[slot].p : nullptr;
+            } else if (mask_format == VI_MASKS_PACKED) {
+                a.seg_bits = h_seg ? (uint32_t*)c->hb_seg[slot].p : nullptr; a.def_bits = h_def ? (uint32_t*)c->hb_def[slot].p : nullptr;
+            }
+            a.rec = (vi_unit_record*)c->hb_rec[slot].p;
+            a.mode = MODE_FULL;
+            int r2;
+            if ((r2 = launch_units(c, a, c->grid, st, slot))) return r2;
+            if (h_seg) CU(cudaMemcpyAsync((uint8_t*)h_seg + (size_t)i0 * ubytes, c->hb_seg[slot].p, (size_t)ubytes * n, cudaMemcpyDeviceToHost, st));
+            if (h_def) CU(cudaMemcpyAsync((uint8_t*)h_def + (size_t)i0 * ubytes, c->hb_def[slot].p, (size_t)ubytes * n, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_rec + (size_t)i0 * n_units, c->hb_rec[slot].p, sizeof(vi_unit_record) * (size_t)n_units * n,
+                               cudaMemcpyDeviceToHost, st));
         }
-        KArgs a;
-        base_args(c, a, c->grid);
-        if ((rc = fill_params(a, params))) return rc;
-        a.frames = (const uint8_t*)c->hb_frames[slot].p; a.n_images = n; a.W = W; a.H = H; a.row_pitch = row_pitch;
-        a.image_stride = image_stride;
-        a.excl = (const vi_excl*)c->d_excl.p; a.n_excl = (int)c->excl.size();
-        a.refc = c->has_refc ? (const double*)c->d_refc.p : nullptr;
-        a.is_reference = c->is_reference;
-        a.seg_out = (uint8_t*)c->hb_seg[slot].p; a.def_out = (uint8_t*)c->hb_def[slot].p; a.rec = (vi_unit_record*)c->hb_rec[slot].p;
-        a.mode = MODE_FULL;
-        if ((rc = launch_units(c, a, c->grid, st, slot))) return rc;
-        if (h_seg) CU(cudaMemcpyAsync(h_seg + (size_t)i0 * upx, c->hb_seg[slot].p, (size_t)upx * n, cudaMemcpyDeviceToHost, st));
-        if (h_def) CU(cudaMemcpyAsync(h_def + (size_t)i0 * upx, c->hb_def[slot].p, (size_t)upx * n, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_rec + (size_t)i0 * n_units, c->hb_rec[slot].p, sizeof(vi_unit_record) * (size_t)n_units * n,
-                           cudaMemcpyDeviceToHost, st));
+        return VI_OK;
+    };
+    rc = run_chunks();
+    // also on failure: nothing may still be writing into the caller's buffers when this returns
+    for (int b = 0; b < kHostSlots; ++b) {
+        cudaError_t e = cudaStreamSynchronize(c->streams[b]);
+        if (e != cudaSuccess && rc == VI_OK) rc = fail(VI_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
     }
-    for (int b = 0; b < kHostSlots; ++b) CU(cudaStreamSynchronize(c->streams[b]));
-    // records carry chunk-local image indices: make them batch-global
-    for (int i0 = 0; i0 < n_images; i0 += chunk) {
-        const int n = std::min(chunk, n_images - i0);
-        for (long long k = 0; k < (long long)n * n_units; ++k) h_rec[(size_t)i0 * n_units + k].image += i0;
-    }
-    return VI_OK;
+    return rc;
+}
+
+extern "C" int vi_inspect_batch_host(vi_ctx* c, const uint8_t* h_frames, int n_images, int W, int H, int64_t row_pitch,
+                                     int64_t image_stride, const vi_params* params, uint8_t* h_seg, uint8_t* h_def,
+                                     vi_unit_record* h_rec) {
+    return host_batch(c, h_frames, n_images, W, H, row_pitch, image_stride, params, VI_MASKS_BYTES, h_seg, h_def, h_rec);
+}
+
+extern "C" int vi_inspect_batch_host_fmt(vi_ctx* c, const uint8_t* h_frames, int n_images, int W, int H, int64_t row_pitch,
+                                         int64_t image_stride, const vi_params* params, int mask_format, void* h_seg,
+                                         void* h_def, vi_unit_record* h_rec) {
+    return host_batch(c, h_frames, n_images, W, H, row_pitch, image_stride, params, mask_format, h_seg, h_def, h_rec);
 }
 
 // ---------------------------------------------------------------------------
@@ -563,9 +794,10 @@ static int compat_run(vi_ctx* c, int mode, const uint8_t* gray, const uint8_t* a
                       long long* out_stats /*[8]*/) {
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
     if (h <= 0 || w <= 0) return fail(VI_ERR_ARG, "array is %dx%d", h, w);
-    CU(cudaSetDevice(c->device));
+    VI_DEVICE(c);
     int32_t rect[4] = {0, 0, w, h};
     int rc;
+    if ((rc = wait_busy_host(c))) return rc;
     cudaStream_t st = c->streams[0];
     if ((rc = set_grid_state(c, c->one, rect, 1, st))) return rc;
     const size_t px = (size_t)w * h;
@@ -667,7 +899,7 @@ static int ingest_common(vi_ctx* c, int fmt, const void* d_src, int n_images, in
     if (n_images <= 0 || W <= 0 || H <= 0) return fail(VI_ERR_ARG, "ingest: n_images=%d W=%d H=%d", n_images, W, H);
     if (src_pitch < (int64_t)W * bpp || dst_pitch < W) return fail(VI_ERR_ARG, "ingest: pitch smaller than a row");
     if (n_images > 1 && (src_stride < src_pitch * H || dst_stride < dst_pitch * H)) return fail(VI_ERR_ARG, "ingest: stride smaller than an image");
-    CU(cudaSetDevice(c->device));
+    VI_DEVICE(c);
     cudaStream_t st = (cudaStream_t)stream;
     const uint8_t* src = (const uint8_t*)d_src;
     const bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)d_dst % 16 == 0) && src_pitch % 16 == 0 && src_stride % 16 == 0 &&

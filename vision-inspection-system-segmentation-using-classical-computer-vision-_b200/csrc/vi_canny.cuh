@@ -63,7 +63,7 @@ VI_PHASE void canny_candidates(const uint8_t* gray, const Geom& g, int low, int 
 }
 
 // EDGES = the 8-components of CAND that hold a STRONG pixel.
-VI_PHASE int canny_hysteresis(CtaScratch& cs, const unsigned* CAND, const unsigned* STRONG, unsigned* EDGES, const Geom& g,
+VI_PHASE int canny_hysteresis(Cta& cs, const unsigned* CAND, const unsigned* STRONG, unsigned* EDGES, const Geom& g,
                                        const CclWs& ws_s, const CclWs& ws_g, CclWs& ws) {
     const int R = ccl_build(cs, CAND, g, true, false, ws_s, ws_g, ws, (PhaseTimerT<false>*)nullptr);
     for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {

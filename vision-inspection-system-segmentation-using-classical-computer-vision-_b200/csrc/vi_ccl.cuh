@@ -90,7 +90,7 @@ __device__ __forceinline__ void run_edges(const unsigned* M, const Geom& g, int 
 // Builds runs + components of mask M.  ws_s (shared) is used when the runs fit,
 // else ws_g (global scratch).  Returns R (run count) and the workspace used.
 template <class PT>
-VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
+VI_PHASE int ccl_build(Cta& cs, const unsigned* M, const Geom& g, bool conn8, bool border,
                        const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PT* pt) {
     const int per = (g.nwords + kThreads - 1) / kThreads;
     const int i0 = threadIdx.x * per;
@@ -128,7 +128,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
     cta_sync();
     if (pt) pt->acc(24);
     const int c8 = conn8 ? 1 : 0;
-    if (threadIdx.x == 0) cs.flag = 0;
+    if (threadIdx.x == 0) cs.s->flag = 0;
     // Fast path: a stack of single runs, one per consecutive row, each touching the one above -- a solid blob, what
     // a filled plate mask is -- is one component by inspection: every run points at run 1 and the union-find is skipped.
     if (!border) {
@@ -139,7 +139,7 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
         }
         if (!cta_sync_or(!ok) && R > 0) {
             for (int i = 1 + threadIdx.x; i <= (int)R; i += kThreads) { ws.parent()[i] = 1; ws.acc0()[i] = 0; ws.acc1()[i] = 0; }
-            if (threadIdx.x == 0) cs.flag = 1;             // one component: ccl_largest sums it directly
+            if (threadIdx.x == 0) cs.s->flag = 1;             // one component: ccl_largest sums it directly
             cta_sync();
             if (pt) pt->acc(25);
             return (int)R;
@@ -204,6 +204,60 @@ VI_PHASE int ccl_build(CtaScratch& cs, const unsigned* M, const Geom& g, bool co
     return (int)R;
 }
 
+// Row scan: the shortcut in front of the labelling passes.  One thread per row finds the row's first / last set pixel
+// and its pixel count (one run <=> count == last - first + 1).
+//   any_multi : some row holds more than one run.  If none does, every background run touches the left or right crop
+//               border, so the mask has no holes (the hole fill is the identity).
+//   solid     : no such row, the occupied rows are consecutive and each run touches the one above (8-connectivity):
+//               the mask is ONE component -- what a filled plate mask and its erosion are -- and area / coordinate
+//               sums come straight from the row table.  No run table, no union-find, no paint.
+// `info` : h words of scratch.
+struct RowScan { bool any_multi, solid; unsigned area; unsigned long long sx, sy; };
+
+VI_PHASE RowScan mask_row_scan(Cta& cs, const unsigned* M, const Geom& g, unsigned* info) {
+    RowScan r;
+    r.any_multi = false; r.solid = false; r.area = 0; r.sx = 0; r.sy = 0;
+    unsigned long long area = 0, sx = 0, sy = 0;
+    int multi = 0;
+    for (int y = threadIdx.x; y < g.h; y += kThreads) {
+        const unsigned* row = M + y * g.wpr;
+        int xs = -1, xe = 0;
+        unsigned n = 0;
+        for (int c = 0; c < g.wpr; ++c) {
+            const unsigned m = row[c];
+            if (m) {
+                if (xs < 0) xs = c * 32 + __ffs(m) - 1;
+                xe = c * 32 + 31 - __clz(m);
+                n += __popc(m);
+            }
+        }
+        info[y] = n ? ((unsigned)xs | ((unsigned)xe << 16)) : 0xffffffffu;
+        if (n) {
+            multi |= (int)n != xe - xs + 1;
+            area += n; sx += (unsigned long long)(xs + xe) * n / 2; sy += (unsigned long long)y * n;
+        }
+    }
+    r.any_multi = cta_sync_or(multi) != 0;          // the barrier also publishes `info`
+    if (r.any_multi) return r;
+    unsigned long long firsts = 0, bad = 0;
+    for (int y = threadIdx.x; y < g.h; y += kThreads) {
+        const unsigned me = info[y];
+        if (me == 0xffffffffu) continue;
+        const unsigned up = y > 0 ? info[y - 1] : 0xffffffffu;
+        if (up == 0xffffffffu) { ++firsts; continue; }
+        const int xs = (int)(me & 0xffffu), xe = (int)(me >> 16), pxs = (int)(up & 0xffffu), pxe = (int)(up >> 16);
+        if (!(xs <= pxe + 1 && xe >= pxs - 1)) bad = 1;
+    }
+    // coordinate sums stay below 2^48 (w, h < 2^16, area < 2^32): the two flag counts ride in the top 16 bits
+    unsigned a32 = (unsigned)area;
+    unsigned long long vx = sx | (firsts << 48), vy = sy | (bad << 48);
+    cta_sum3(cs, a32, vx, vy);
+    r.area = a32;
+    r.solid = (vx >> 48) == 1u && (vy >> 48) == 0u;
+    r.sx = vx & 0xffffffffffffull; r.sy = vy & 0xffffffffffffull;
+    return r;
+}
+
 // Warp-aggregated per-root accumulation: lanes whose root equals the first valid
 // lane's root are reduced with REDUX and added once; the rest add individually.
 __device__ __forceinline__ void agg_add(unsigned* acc, bool valid, int root, unsigned val) {
@@ -259,19 +313,19 @@ VI_PHASE void ccl_paint(unsigned* dst, const unsigned* base, const Geom& g, cons
 // Largest component (max area; ties -> smallest 2x2-block key, i.e. OpenCV's label
 // order).  Returns the root id (0 if there is no run) and its area /
 // coordinate sums through the out-params.  Uses acc0 = area, acc1 = min block key.
-VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
+VI_PHASE int ccl_largest(Cta& cs, const Geom& g, const CclWs& ws, int R,
                                   unsigned& area, unsigned long long& sum_x, unsigned long long& sum_y) {
     area = 0; sum_x = 0; sum_y = 0;
     if (R == 0) return 0;
-    if (cs.flag) {                                  // ccl_build found a single solid component (root = run 1)
+    if (cs.s->flag) {                                  // ccl_build found a single solid component (root = run 1)
         unsigned long long a = 0, sx = 0, sy = 0;
         for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {
             const unsigned long long xs = ws.xs()[i], xe = ws.xe()[i], len = xe - xs + 1;
             a += len; sx += (xs + xe) * len / 2; sy += (unsigned long long)ws.yy()[i] * len;
         }
-        area = (unsigned)cta_sum_u64(cs, a);
-        sum_x = cta_sum_u64(cs, sx);
-        sum_y = cta_sum_u64(cs, sy);
+        unsigned a32 = (unsigned)a;
+        cta_sum3(cs, a32, sx, sy);
+        area = a32; sum_x = sx; sum_y = sy;
         return 1;
     }
     const int Rpad = (R + kThreads - 1) / kThreads * kThreads;
@@ -319,8 +373,9 @@ VI_PHASE int ccl_largest(CtaScratch& cs, const Geom& g, const CclWs& ws, int R,
             sx += (xs + xe) * len / 2;
             sy += (unsigned long long)ws.yy()[i] * len;
         }
-    sum_x = cta_sum_u64(cs, sx);
-    sum_y = cta_sum_u64(cs, sy);
+    unsigned long long v2[2] = {sx, sy};
+    cta_sum_n<2>(cs, v2);
+    sum_x = v2[0]; sum_y = v2[1];
     area = amax;
     return broot;
 }

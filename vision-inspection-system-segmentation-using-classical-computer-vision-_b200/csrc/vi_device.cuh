@@ -22,6 +22,7 @@ constexpr int kOtsuWarp = kWarps - 1;   // this warp advances the exact Otsu rec
 constexpr int kHistWords = 2048;   // per-warp lane-private histogram: [64 bin-quads][32 lanes] u32, 4 x 8-bit counters
 constexpr int kHistBytes = kHistWords * 4;
 constexpr int kMaxExcl = 32;
+constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch domain that exchange record tables
 constexpr int kMaxTaps = 33;
 constexpr int kMaxSE = 33;
 constexpr int kMaxAdapt = 201;      // widest adaptive-threshold block (the reference's widget range, indexing_ui.py:805)
@@ -93,7 +94,7 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
     int cpitch = ((wmax + 2) / 3 + 2) & ~1;
     int rch = wmax <= 352 ? 11 : 15;
-    int band = wmax <= 480 ? 16 * (32 * rch + 2) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
+    int band = wmax <= 480 ? 16 * (32 * rch + 3) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
     int otsu = 3 * 256 * 8 + 64;                // vi_pipeline.cuh: kOtsuWsBytes, at the end of the workspace
     band += otsu;                               // the Otsu warp works next to the rank-count cell pass
     int rowfirst = align16((hmax + 2) * 4);
@@ -119,6 +120,41 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     if (p->run_cap > 65534) p->run_cap = 65534;
     p->total = p->gray_bytes + r_bytes;
     return true;
+}
+
+// Plan for units that do not fit one SM's shared memory: the same regions, laid out in a per-CTA arena in global memory
+// (L2-resident for mid-size units); only the lane-private histogram copies stay in shared memory.  `total` is the
+// dynamic shared memory (the histogram copies), the arena needs gray_bytes + kNumMasks * mask_bytes + ws_bytes.
+// Bounds of a unit: 255 * pixels must fit 32 bits (histogram moments), and the index arithmetic of the phases
+// (magic_div: n * d < 2^32) holds for w <= 4096, h <= 8192.  A whole 4096x3000 frame is a legal unit.
+constexpr long long kMaxUnitPixels = 1ll << 24;
+constexpr int kMaxUnitW = 4096, kMaxUnitH = 8192;
+
+__host__ inline bool make_plan_gmem(int wmax, int hmax, SmemPlan* p, int gray_need, int mask_words_need) {
+    if ((long long)wmax * hmax > kMaxUnitPixels || wmax > kMaxUnitW || hmax > kMaxUnitH) return false;
+    Geom g = make_geom(wmax, hmax);
+    p->gray_bytes = align16(gray_need > 0 ? gray_need : g.gp * hmax);
+    p->mask_bytes = align16((mask_words_need > 0 ? mask_words_need : g.nwords) * 4);
+    p->band_pitch = 0;
+    int cpitch = ((wmax + 2) / 3 + 2) & ~1;
+    int rch = wmax <= 352 ? 11 : 15;
+    int band = wmax <= 480 ? 16 * (32 * rch + 3) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
+    int otsu = 3 * 256 * 8 + 64;
+    int rowfirst = align16((hmax + 2) * 4);
+    int want_cap = 8192;
+    int ccl = rowfirst + (want_cap + 1) * 18 + 64;
+    int ws = band + otsu;
+    if (ccl > ws) ws = ccl;
+    p->ws_bytes = align16(ws);
+    p->run_cap = (p->ws_bytes - rowfirst - 64) / 18 - 1;
+    if (p->run_cap > 65534) p->run_cap = 65534;
+    p->n_hist = kWarps;
+    p->total = kWarps * kHistBytes;
+    return true;
+}
+
+__host__ inline long long plan_arena_bytes(const SmemPlan& p) {
+    return ((long long)p.gray_bytes + (long long)kNumMasks * p.mask_bytes + p.ws_bytes + 255) & ~255ll;
 }
 
 struct KArgs {
@@ -155,7 +191,17 @@ struct KArgs {
     long long scratch_rank_off;     // offset of the rank-count lists (dirty cells, ambiguous pixels)
     int wmax, hmax;
     long long* seg_stats;           // optional: [n_total][3] area, sum x, sum y of the final seg mask (CSV export), or null
-    long long* prof;                // diagnostics: [n_total][32] per-phase cycle counts, or null
+    uint32_t* seg_bits;             // optional packed-bit masks (1 bit per pixel, rows of wpr words, PNG bit order), or null
+    uint32_t* def_bits;
+    const long long* unit_woff;     // [n_units+1] word offsets of the packed-bit masks inside one image's block
+    long long unit_words;
+    int image_base;                 // records carry image = img * image_mul + image_base (chunked host-buffer call: base;
+    int image_mul;                  //  a rank's shard of a multi-GPU job: global index = rank + k * world)
+    vi_unit_record* peer_rec[kMaxPeers];   // record tables of all ranks (own included), peer-mapped: the record of global
+    int n_peers;                    //  image g, unit u is stored at [g * n_units + u] of every one of them, or 0
+    uint8_t* arena;                 // GMEM kernel: per-CTA global arena holding what the shared-memory plan holds
+    long long arena_stride;         //  (gray crop, masks, workspace) for units larger than one SM's shared memory
+    long long* prof;                // diagnostics: [n_total][kProfSlots] per-phase cycle counts, or null
     SmemPlan plan;
 };
 
@@ -163,17 +209,29 @@ struct KArgs {
 // CTA-wide primitives
 // ---------------------------------------------------------------------------
 struct CtaScratch {
-    unsigned wa[kWarps];
-    unsigned wb[kWarps];
-    unsigned long long wl[kWarps];
-    unsigned tot_a, tot_b;
-    unsigned long long tot_l;
+    // two buffers, used alternately: a collective writes its partials, passes ONE barrier and every warp reduces the
+    // kWarps partials on its own; the next collective uses the other buffer, so no trailing barrier is needed (a warp
+    // can only reach the call after next by passing the next call's barrier, i.e. after everybody's reads of this one).
+    // Kept small: every byte of static shared memory comes out of the histogram copies (vi_device.cuh: make_plan).
+    unsigned long long wl[2][2][kWarps];
+    unsigned w32[2][kWarps];
     int flag;
+};
+
+// Thread-local handle of the CTA collectives: the shared scratch and the buffer parity (uniform over the CTA because
+// every thread runs the same sequence of collectives).
+struct Cta {
+    CtaScratch* s;
+    unsigned par;
+    // asynchronous crop gather (vi_pipeline.cuh: gather_issue / gather_finish): phase parity of its mbarrier and whether
+    // the next unit's rows are in flight (uniform over the CTA)
+    unsigned gpar;
+    int gpending;
 };
 
 // Diagnostics: per-phase SM cycle counts of one unit (thread 0, after the barrier
 // that ends the phase), written only when KArgs::prof is set.
-constexpr int kProfSlots = 32;
+constexpr int kProfSlots = 40;
 struct PtState { long long* out; long long t; int k; int pad; };      // lives in shared memory: no registers held across phases
 // ON = false compiles every hook away (the production kernel); ON = true is the diagnostics kernel that
 // vi_debug_set_profile selects.
@@ -208,9 +266,10 @@ __device__ __forceinline__ int cta_sync_or(int pred) { return __syncthreads_or(p
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
-// Exclusive scan of (a, b) over the CTA's threads; totals returned through ta/tb.
-__device__ inline void cta_excl_scan2(CtaScratch& cs, unsigned& a, unsigned& b, unsigned& ta, unsigned& tb) {
+// Exclusive scan of (a, b) over the CTA's threads; totals returned through ta/tb.  One barrier.
+__device__ inline void cta_excl_scan2(Cta& c, unsigned& a, unsigned& b, unsigned& ta, unsigned& tb) {
     const int lane = lane_id(), warp = warp_id();
+    const unsigned p = c.par; c.par ^= 1u;
     unsigned ia = a, ib = b;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -218,69 +277,84 @@ __device__ inline void cta_excl_scan2(CtaScratch& cs, unsigned& a, unsigned& b, 
         unsigned xb = __shfl_up_sync(kFull, ib, o);
         if (lane >= o) { ia += xa; ib += xb; }
     }
-    if (lane == 31) { cs.wa[warp] = ia; cs.wb[warp] = ib; }
+    if (lane == 31) c.s->wl[p][0][warp] = (unsigned long long)ia | ((unsigned long long)ib << 32);
     cta_sync();
-    if (warp == 0) {
-        unsigned va = lane < kWarps ? cs.wa[lane] : 0u;
-        unsigned vb = lane < kWarps ? cs.wb[lane] : 0u;
-        unsigned sa = va, sb = vb;
+    const unsigned long long pv = lane < kWarps ? c.s->wl[p][0][lane] : 0ull;
+    const unsigned va = (unsigned)pv, vb = (unsigned)(pv >> 32);
+    unsigned sa = va, sb = vb;
 #pragma unroll
-        for (int o = 1; o < kWarps; o <<= 1) {
-            unsigned xa = __shfl_up_sync(kFull, sa, o);
-            unsigned xb = __shfl_up_sync(kFull, sb, o);
-            if (lane >= o) { sa += xa; sb += xb; }
-        }
-        if (lane < kWarps) { cs.wa[lane] = sa - va; cs.wb[lane] = sb - vb; }
-        if (lane == kWarps - 1) { cs.tot_a = sa; cs.tot_b = sb; }
+    for (int o = 1; o < kWarps; o <<= 1) {
+        unsigned xa = __shfl_up_sync(kFull, sa, o);
+        unsigned xb = __shfl_up_sync(kFull, sb, o);
+        if (lane >= o) { sa += xa; sb += xb; }
     }
-    cta_sync();
-    a = ia - a + cs.wa[warp];
-    b = ib - b + cs.wb[warp];
-    ta = cs.tot_a;
-    tb = cs.tot_b;
-    cta_sync();
+    ta = __shfl_sync(kFull, sa, kWarps - 1);
+    tb = __shfl_sync(kFull, sb, kWarps - 1);
+    a = ia - a + __shfl_sync(kFull, sa - va, warp);
+    b = ib - b + __shfl_sync(kFull, sb - vb, warp);
 }
 
-__device__ inline unsigned long long cta_sum_u64(CtaScratch& cs, unsigned long long v) {
+// Sums over the CTA, one barrier for all of them: v[0], v[1] 64-bit; cta_sum3 adds a 32-bit value in front.
+template <int N>
+__device__ __forceinline__ void cta_sum_n(Cta& c, unsigned long long (&v)[N]) {
+    static_assert(N >= 1 && N <= 2, "cta_sum_n: 1..2 values");
     const int lane = lane_id(), warp = warp_id();
+    const unsigned p = c.par; c.par ^= 1u;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
-    if (lane == 0) cs.wl[warp] = v;
-    cta_sync();
-    if (warp == 0) {
-        unsigned long long t = lane < kWarps ? cs.wl[lane] : 0ull;
+    for (int k = 0; k < N; ++k) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(kFull, t, o);
-        if (lane == 0) cs.tot_l = t;
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(kFull, v[k], o);
+        if (lane == 0) c.s->wl[p][k][warp] = v[k];
     }
     cta_sync();
-    unsigned long long r = cs.tot_l;
-    cta_sync();
-    return r;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        unsigned long long t = lane < kWarps ? c.s->wl[p][k][lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+        v[k] = t;
+    }
 }
 
-__device__ inline unsigned long long cta_max_u64(CtaScratch& cs, unsigned long long v) {
+__device__ __forceinline__ void cta_sum3(Cta& c, unsigned& a, unsigned long long& b, unsigned long long& d) {
     const int lane = lane_id(), warp = warp_id();
+    const unsigned p = c.par; c.par ^= 1u;
+    a = __reduce_add_sync(kFull, a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { b += __shfl_down_sync(kFull, b, o); d += __shfl_down_sync(kFull, d, o); }
+    if (lane == 0) { c.s->w32[p][warp] = a; c.s->wl[p][0][warp] = b; c.s->wl[p][1][warp] = d; }
+    cta_sync();
+    unsigned ta = lane < kWarps ? c.s->w32[p][lane] : 0u;
+    unsigned long long tb = lane < kWarps ? c.s->wl[p][0][lane] : 0ull, td = lane < kWarps ? c.s->wl[p][1][lane] : 0ull;
+    a = __reduce_add_sync(kFull, ta);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { tb += __shfl_xor_sync(kFull, tb, o); td += __shfl_xor_sync(kFull, td, o); }
+    b = tb; d = td;
+}
+
+__device__ inline unsigned long long cta_sum_u64(Cta& c, unsigned long long v) {
+    unsigned long long a[1] = {v};
+    cta_sum_n<1>(c, a);
+    return a[0];
+}
+
+__device__ inline unsigned long long cta_max_u64(Cta& c, unsigned long long v) {
+    const int lane = lane_id(), warp = warp_id();
+    const unsigned p = c.par; c.par ^= 1u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long x = __shfl_down_sync(kFull, v, o);
         v = x > v ? x : v;
     }
-    if (lane == 0) cs.wl[warp] = v;
+    if (lane == 0) c.s->wl[p][0][warp] = v;
     cta_sync();
-    if (warp == 0) {
-        unsigned long long t = lane < kWarps ? cs.wl[lane] : 0ull;
+    unsigned long long t = lane < kWarps ? c.s->wl[p][0][lane] : 0ull;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long x = __shfl_down_sync(kFull, t, o);
-            t = x > t ? x : t;
-        }
-        if (lane == 0) cs.tot_l = t;
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_xor_sync(kFull, t, o);
+        t = x > t ? x : t;
     }
-    cta_sync();
-    unsigned long long r = cs.tot_l;
-    cta_sync();
-    return r;
+    return t;
 }
 
 // ---------------------------------------------------------------------------
@@ -467,7 +541,7 @@ __device__ __forceinline__ unsigned swar_gt(unsigned W, const SwarPivot& q) { re
 // The four bit-7 flags of a word as a nibble (bit k = byte k): one multiply lines them up at bits 28..31.
 __device__ __forceinline__ unsigned swar_nibble(unsigned f7) { return (f7 * 0x00204081u) >> 28; }
 
-__device__ inline unsigned cta_popcount(CtaScratch& cs, const unsigned* M, const Geom& g) {
+__device__ inline unsigned cta_popcount(Cta& cs, const unsigned* M, const Geom& g) {
     unsigned long long n = 0;
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) n += __popc(M[i]);
     return (unsigned)cta_sum_u64(cs, n);

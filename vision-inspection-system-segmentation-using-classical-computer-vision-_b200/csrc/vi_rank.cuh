@@ -66,7 +66,7 @@ struct RankWs {
 // the V lanes that own no column), so no access needs a bounds test (a prefix only flows forward: what lies
 // past column w-1 is never read back).
 __host__ __device__ inline int rank_ch(int w) { return w <= 352 ? 11 : 15; }
-__host__ __device__ inline int rank_P(int w) { return 32 * rank_ch(w) + 2; }
+__host__ __device__ inline int rank_P(int w) { return 32 * rank_ch(w) + 3; }      // odd: see rank_group_cells
 __host__ __device__ inline int rank_cpitch(int w) { return ((w + kCell - 1) / kCell + 2) & ~1; }      // cells + a dummy slot
 __host__ __device__ inline int rank_ws_bytes(int w) {
     return kLatBand * rank_P(w) * 8 + kCmmRows * rank_cpitch(w) * 2 + 64 * 4;
@@ -178,60 +178,50 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
 // gray q as (q, 255 - q) 16-bit halves: the packed minimum carries min and 255 - max.
 __device__ __forceinline__ unsigned mm_pack(unsigned q) { return q * 0xFFFF0001u + 0x00FF0000u; }
 
-// S + C for one lattice row (one warp).  CH = columns per lane of the prefix pass (odd).
-template <int CH>
-__device__ __forceinline__ void rank_row_cells(const Geom& g, RankWs& w, uint2* row, const unsigned short* cm, int cj, int nlx) {
-    const int lane = lane_id();
+// S + C for a group of kGrp consecutive cells of one lattice row (one thread).  The window of cell i is columns
+// 3i-9 .. 3i+11 = the seven 3-column cells i-3 .. i+3 (columns outside the crop replicate the edge column: clamped
+// indices), so a thread adds 3 * (kGrp + 6) column sums into cell sums, forms the first window from seven of them and
+// slides it over the group.  No prefix pass, no cross-lane traffic: every load is independent of the others.
+// Threads of a half-warp hold the 16 rows of a band (the row pitch P is odd: their 8-byte loads hit distinct banks).
+constexpr int kGrp = 4;
+static_assert(kLatBand == 16, "the S+C pass maps the 16 lanes of a half-warp to the rows of a band");
+
+template <bool EDGE>
+__device__ __forceinline__ void rank_group_cells(const Geom& g, RankWs& w, const uint2* row, const unsigned short* cm, int cj,
+                                                 int gi, int nlx, bool active) {
     const int wm1 = g.w - 1;
-    {   // ---- S: inclusive prefix over the row ---------------------------------------
-        uint2* chunk = row + lane * CH;
-        uint2 v[CH];
-        unsigned a0 = 0, a1 = 0;
+    const int c0 = kCell * kGrp * gi - 9;
+    uint2 cs[kGrp + 6];
 #pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            const uint2 t = chunk[k];
-            a0 += t.x; a1 += t.y;
-            v[k] = make_uint2(a0, a1);
-        }
-        unsigned e0 = a0, e1 = a1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y0 = __shfl_up_sync(kFull, e0, o), y1 = __shfl_up_sync(kFull, e1, o);
-            if (lane >= o) { e0 += y0; e1 += y1; }
-        }
-        e0 -= a0; e1 -= a1;
-#pragma unroll
-        for (int k = 0; k < CH; ++k) chunk[k] = make_uint2(v[k].x + e0, v[k].y + e1);
+    for (int k = 0; k < kGrp + 6; ++k) {
+        const int c = c0 + kCell * k;
+        uint2 t0, t1, t2;
+        if (EDGE) { t0 = row[min(max(c, 0), wm1)]; t1 = row[min(max(c + 1, 0), wm1)]; t2 = row[min(max(c + 2, 0), wm1)]; }
+        else { t0 = row[c]; t1 = row[c + 1]; t2 = row[c + 2]; }
+        cs[k] = make_uint2(t0.x + t1.x + t2.x, t0.y + t1.y + t2.y);
     }
-    __syncwarp();
-    // ---- C: one lane per cell -------------------------------------------------------
-    const uint2 first = row[0];
-    uint2 last = row[wm1];
-    { const uint2 l2 = row[wm1 - 1]; last.x -= l2.x; last.y -= l2.y; }
-    for (int i0 = 0; i0 < nlx; i0 += 32) {
-        const int i = min(i0 + lane, nlx - 1);                       // surplus lanes repeat the last cell
-        const int a = kCell * i - 9, b = kCell * i + 11;            // window columns (clamped to the crop)
-        const uint2 hi = row[min(b, wm1)], lo = row[max(a, 0) - 1];
-        const unsigned nl = (unsigned)max(-a, 0), nr = (unsigned)max(b - wm1, 0);      // replicated edge columns
-        const unsigned C0 = hi.x - lo.x + nl * first.x + nr * last.x;
-        const unsigned C1 = hi.y - lo.y + nl * first.y + nr * last.y;
+    unsigned C0 = 0, C1 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { C0 += cs[k].x; C1 += cs[k].y; }
+    const int lane = lane_id();
+#pragma unroll
+    for (int m = 0; m < kGrp; ++m) {
+        const int i = kGrp * gi + m;
+        const int ic = min(i, nlx - 1);
         const int n263 = __popc((C0 + kGe263) & kFlag) + __popc((C1 + kGe263) & kFlag);
         const int n179 = __popc((C0 + kGe179) & kFlag) + __popc((C1 + kGe179) & kFlag);
         const unsigned cw = w.table[n179 * 7 + n263];
-        const unsigned mmv = cm[i];
+        const unsigned mmv = cm[ic];
         const unsigned mn = mmv & 255u, mx = 255u - (mmv >> 8);
-        const bool dirty = (i0 + lane < nlx) && (mn < ((cw >> 8) & 255u) || mx > ((cw >> 16) & 255u));
-        // append the dirty cells (one atomic per warp)
+        const bool dirty = active && i < nlx && (mn < ((cw >> 8) & 255u) || mx > ((cw >> 16) & 255u));
         const unsigned dm = __ballot_sync(kFull, dirty);
-        if (dm) {
+        if (dm) {                                                    // append the dirty cells (one atomic per warp)
             int base = 0;
             if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
             base = __shfl_sync(kFull, base, 0);
-            if (dirty) {
-                const int slot = base + __popc(dm & ((1u << lane) - 1u));
-                w.dirty[slot] = make_uint2(((unsigned)cj << 16) | (unsigned)i, cw);
-            }
+            if (dirty) w.dirty[base + __popc(dm & ((1u << lane) - 1u))] = make_uint2(((unsigned)cj << 16) | (unsigned)i, cw);
         }
+        if (m + 1 < kGrp) { C0 += cs[m + 7].x - cs[m].x; C1 += cs[m + 7].y - cs[m].y; }
     }
 }
 
@@ -374,12 +364,23 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
         }
         cta_sync();
         pt.acc(20);
-        // ---- S + C: one warp per lattice row ------------------------------------------
-        for (int jj = warp; jj < j1 - j0; jj += kWarps) {
-            uint2* row = w.cs + jj * w.P + 1;
-            const unsigned short* cm = w.cmm + par * bufrows + jj * w.cpitch;
-            if (g.w <= 352) rank_row_cells<11>(g, w, row, cm, j0 + jj, nlx);
-            else rank_row_cells<15>(g, w, row, cm, j0 + jj, nlx);
+        // ---- S + C: one thread per (lattice row of the band, group of kGrp cells) --------------
+        {
+            const int ngrp = (nlx + kGrp - 1) / kGrp;
+            const int jj = threadIdx.x & (kLatBand - 1);
+            const bool rowok = jj < j1 - j0;
+            const uint2* row = w.cs + (rowok ? jj : 0) * w.P + 1;
+            const unsigned short* cm = w.cmm + par * bufrows + (rowok ? jj : 0) * w.cpitch;
+            for (int gb = 0; gb < ngrp; gb += kThreads / kLatBand) {
+                const int gi = gb + (threadIdx.x >> 4);                     // uniform over a half-warp
+                const bool active = rowok && gi < ngrp;
+                const int gic = min(gi, ngrp - 1);
+                const int c0 = kCell * kGrp * gic - 9;
+                // warp-uniform choice (the two half-warps hold different groups; the ballots inside need the whole warp)
+                const bool inner = __all_sync(kFull, c0 >= 0 && c0 + kCell * (kGrp + 6) - 1 <= g.w - 1);
+                if (inner) rank_group_cells<false>(g, w, row, cm, j0 + jj, gic, nlx, active);
+                else rank_group_cells<true>(g, w, row, cm, j0 + jj, gic, nlx, active);
+            }
         }
         cta_sync();
         pt.acc(21);

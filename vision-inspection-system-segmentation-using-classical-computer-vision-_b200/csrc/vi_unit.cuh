@@ -11,7 +11,7 @@ namespace vi {
 
 // Canonical (raster-order) label of every root: 1 + number of roots with a smaller
 // run id.  Stored in acc1[root]; returns the number of components.
-VI_PHASE int ccl_rank_roots(CtaScratch& cs, const CclWs& ws, int R) {
+VI_PHASE int ccl_rank_roots(Cta& cs, const CclWs& ws, int R) {
     unsigned carry = 0;
     for (int base = 0; base < R; base += kThreads) {
         int i = base + threadIdx.x + 1;
@@ -70,6 +70,16 @@ VI_PHASE void store_mask_bytes_sparse(const unsigned* M, const Geom& g, uint8_t*
             if (nib) row[k] = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
         }
     }
+}
+
+// Packed-bit mask out: rows of wpr 32-bit words; inside every byte the first pixel is the most significant bit (the bit
+// order of a 1-bit PNG scanline and of numpy.unpackbits).  The kernel's own words hold pixel x at bit x & 31.
+VI_PHASE void store_mask_words(const unsigned* M, const Geom& g, uint32_t* __restrict__ dst) {
+    for (int i = threadIdx.x; i < g.nwords; i += kThreads) dst[i] = __byte_perm(__brev(M[i]), 0u, 0x0123u);
+}
+
+VI_PHASE void zero_words(uint32_t* __restrict__ dst, int n) {
+    for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = 0u;
 }
 
 // L2 prefetch of a unit's crop rows (issued for the CTA's next unit while this one computes).
@@ -133,7 +143,7 @@ __device__ inline void select_levels(UnitShared& sh, int npix, int thr, int t) {
 }
 
 // Area and coordinate sums of a bit mask (segmentation.mask_stats, segmentation.py:103-111: the caller divides).
-__device__ inline void mask_sums(CtaScratch& cs, const unsigned* M, const Geom& g, long long* out3) {
+__device__ inline void mask_sums(Cta& cs, const unsigned* M, const Geom& g, long long* out3) {
     unsigned long long n = 0, sx = 0, sy = 0;
     for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
         int y, c; word_rc(g, i, y, c);
@@ -143,8 +153,9 @@ __device__ inline void mask_sums(CtaScratch& cs, const unsigned* M, const Geom& 
                              8 * __popc(m & 0xFF00FF00u) + 16 * __popc(m & 0xFFFF0000u);
         n += pc; sx += (unsigned long long)pc * (c * 32) + pos; sy += (unsigned long long)pc * y;
     }
-    n = cta_sum_u64(cs, n); sx = cta_sum_u64(cs, sx); sy = cta_sum_u64(cs, sy);
-    if (threadIdx.x == 0) { out3[0] = (long long)n; out3[1] = (long long)sx; out3[2] = (long long)sy; }
+    unsigned n32 = (unsigned)n;
+    cta_sum3(cs, n32, sx, sy);
+    if (threadIdx.x == 0) { out3[0] = (long long)n32; out3[1] = (long long)sx; out3[2] = (long long)sy; }
 }
 
 __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, int otsu_t, unsigned seg_area,
@@ -152,22 +163,45 @@ __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, 
                                     double cx, double cy, int n_amb, int n_runs) {
     if (threadIdx.x == 0 && a.rec) {
         vi_unit_record r;
-        r.image = img; r.unit = unit; r.otsu_t = otsu_t; r.seg_area = (int)seg_area; r.roi_area = (int)roi_area;
+        r.image = img * a.image_mul + a.image_base; r.unit = unit; r.otsu_t = otsu_t; r.seg_area = (int)seg_area; r.roi_area = (int)roi_area;
         r.defect_area = (int)defect_area; r.n_kept = n_kept; r.status = status; r.dx = dx; r.dy = dy;
         r.cx = cx; r.cy = cy; r.n_ambiguous = n_amb; r.n_runs = n_runs;
         a.rec[uid] = r;
     }
+    // Multi-GPU: the verdict table is gathered by the kernel itself -- the record goes straight into every rank's table
+    // over NVLink (plain stores to peer-mapped memory; they are posted, nothing waits on them), so no collective runs
+    // between steps.  One lane per peer.
+    if (threadIdx.x < a.n_peers && a.rec) {
+        vi_unit_record r;
+        r.image = img * a.image_mul + a.image_base; r.unit = unit; r.otsu_t = otsu_t; r.seg_area = (int)seg_area; r.roi_area = (int)roi_area;
+        r.defect_area = (int)defect_area; r.n_kept = n_kept; r.status = status; r.dx = dx; r.dy = dy;
+        r.cx = cx; r.cy = cy; r.n_ambiguous = n_amb; r.n_runs = n_runs;
+        a.peer_rec[threadIdx.x][(long long)r.image * a.n_units + unit] = r;
+    }
 }
 
-template <bool PROF>
-__device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned char* smem, UnitShared& sh) {
+// SPEC: the instantiation for the reference's default configuration (full path, Otsu, 3x3 blur, 3x3 cross, threshold
+// method, lattice rank stage, 16-byte aligned frames, no optional outputs): everything that is a run-time choice in
+// the general kernel is a constant here, so the non-default branches are not even in the code (a third of the
+// instructions, less pressure on the instruction cache and on registers).  The host picks it (vi_api.cu: launch_units).
+// GMEM: the instantiation for units beyond one SM's shared memory -- `smem` is then the CTA's arena in global memory
+// (same layout, make_plan_gmem) and `hist_smem` the shared-memory home of the histogram copies.
+template <bool PROF, bool SPEC, bool GMEM>
+__device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned char* smem, unsigned char* hist_smem, UnitShared& sh, Cta& cta) {
     const int tid = threadIdx.x;
     const int img = uid / a.n_units, unit = uid - img * a.n_units;
     const int4 rc = a.rects[unit];
     const Geom g = make_geom(rc.z, rc.w);
     const SmemPlan& plan = a.plan;
     const int npix = g.w * g.h;
-    const int mode = a.mode;
+    const int mode = SPEC ? (int)MODE_FULL : a.mode;
+    const int cfg_blur_k = SPEC ? 3 : a.blur_k;
+    const int cfg_se_k = SPEC ? 3 : a.se_k;
+    const int cfg_seg_method = SPEC ? 0 : a.p.seg_method;
+    const int cfg_defect_method = SPEC ? 0 : a.p.defect_method;
+    long long* const cfg_seg_stats = SPEC ? nullptr : a.seg_stats;
+    uint32_t* const cfg_seg_bits = SPEC ? nullptr : a.seg_bits;
+    uint32_t* const cfg_def_bits = SPEC ? nullptr : a.def_bits;
 
     uint8_t* gray = smem;
     unsigned char* Rg = smem + plan.gray_bytes;
@@ -194,9 +228,11 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     const long long moff = (long long)img * a.unit_px + a.unit_off[unit];
     uint8_t* seg_out = a.seg_out ? a.seg_out + moff : nullptr;
     uint8_t* def_out = a.def_out ? a.def_out + moff : nullptr;
-    int32_t* lab_out = a.labels_out ? a.labels_out + moff : nullptr;
-    const uint8_t* aux = a.aux_mask ? a.aux_mask + moff : nullptr;
-    long long* stats = a.stats_out ? a.stats_out + (long long)uid * 8 : nullptr;
+    int32_t* lab_out = (!SPEC && a.labels_out) ? a.labels_out + moff : nullptr;
+    const uint8_t* aux = (!SPEC && a.aux_mask) ? a.aux_mask + moff : nullptr;
+    long long* stats = (!SPEC && a.stats_out) ? a.stats_out + (long long)uid * 8 : nullptr;
+    // packed-bit outputs: derived on use (nothing of them is held across phases)
+    auto bits_at = [&a, img, unit](uint32_t* base) { return base + ((long long)img * a.unit_words + a.unit_woff[unit]); };
 
     PhaseTimerT<PROF> pt;
     pt.start(&sh.pt, a.prof ? a.prof + (long long)uid * kProfSlots : nullptr);
@@ -208,7 +244,13 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
 
     if (need_gray) {
         const uint8_t* src = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
-        if ((a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0)
+        if (SPEC && cta.gpending) {
+            // the rows were fetched by the bulk-copy engine while the previous unit finished (gather_issue below)
+            mbar_wait(&sh.gather_mbar, cta.gpar);
+            pt.acc(32);
+            gather_finish(src, a.row_pitch, g, gray);
+            cta.gpar ^= 1u; cta.gpending = 0;
+        } else if (SPEC || ((a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0))
             load_gray16(src, a.row_pitch, g, gray);
         else
             load_gray(src, a.row_pitch, g, gray);
@@ -216,28 +258,30 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         cta_sync();
         pt.tick();   // 0 gather
         // ---- P1: blur + histogram ------------------------------------------------
-        int src_mode = (mode == MODE_DETECT || a.blur_k == 0) ? 0 : (a.blur_k == 3 ? 1 : 2);
-        const bool adaptive = need_seg && a.p.seg_method == 1;
+        int src_mode = (mode == MODE_DETECT || cfg_blur_k == 0) ? 0 : (cfg_blur_k == 3 ? 1 : 2);
+        const bool adaptive = need_seg && cfg_seg_method == 1;
         if (adaptive) {
             // the adaptive mean reads the blurred crop from global scratch whatever the blur size
-            if (a.blur_k == 0) {
+            if (cfg_blur_k == 0) {
                 for (int e = tid; e < npix; e += kThreads) { const int y = e / g.w; g_blur[e] = gray[y * g.gp + (e - y * g.w)]; }
                 cta_sync();
             } else {
-                blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
+                blur_general(gray, g, cfg_blur_k, a.taps, g_hp, g_blur);
             }
             src_mode = 2;
         } else if (src_mode == 2) {
-            blur_general(gray, g, a.blur_k, a.taps, g_hp, g_blur);
+            blur_general(gray, g, cfg_blur_k, a.taps, g_hp, g_blur);
         }
-        unsigned* hist_base = reinterpret_cast<unsigned*>(Rg);
+        unsigned* hist_base = reinterpret_cast<unsigned*>(GMEM ? hist_smem : Rg);
         for (int i = tid; i < plan.n_hist * kHistWords; i += kThreads) hist_base[i] = 0;
         if (tid < 256) sh.hist[tid] = 0;
         cta_sync();
-        if (src_mode == 1 && plan.n_hist >= kWarps / 2) {
+        pt.acc(30);
+        if (SPEC || (src_mode == 1 && plan.n_hist >= kWarps / 2)) {
             // default path: one histogram round on min(16, n_hist) warps
             blur3_hist(gray, g, hist_base + warp_id() * kHistWords, min(plan.n_hist, kWarps));
             cta_sync();
+            pt.acc(31);
             hist_collect(hist_base, min(plan.n_hist, kWarps), sh.hist, false);
             cta_sync();
         } else {
@@ -256,8 +300,8 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         // the others walk the columns of the median stage's cell pass, which needs no mask and only approximate
         // levels (an approximate threshold splits the histogram into its classes).
         double* ows = reinterpret_cast<double*>(WS + plan.ws_bytes - kOtsuWsBytes);
-        const bool lattice = (mode == MODE_FULL || mode == MODE_DETECT) && a.p.defect_method == 0 && g.w <= kRankMaxW &&
-                             rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes;
+        const bool lattice = SPEC || ((mode == MODE_FULL || mode == MODE_DETECT) && cfg_defect_method == 0 && g.w <= kRankMaxW &&
+                                      rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes);
         RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
         if (warp_id() == 0) {                       // one warp, no barriers in between: approximate threshold, levels, tables
             int last;
@@ -300,32 +344,41 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             cta_sync();
             pt.tick();   // 4 threshold
             // ---- P4: close, open --------------------------------------------------
-            if (a.se_k == 3) {
+            if (cfg_se_k == 3) {
                 cross3_pass<false>(MA, MB, g); cta_sync();
                 cross3_pass<true>(MB, MA, g); cta_sync();
                 cross3_pass<true>(MA, MB, g); cta_sync();
                 cross3_pass<false>(MB, MA, g); cta_sync();
-            } else if (a.se_k > 0) {
-                se_pass<false>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
-                se_pass<true>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
-                se_pass<true>(MA, MB, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
-                se_pass<false>(MB, MA, g, a.se_k, a.se_lo, a.se_hi); cta_sync();
+            } else if (cfg_se_k > 0) {
+                se_pass<false>(MA, MB, g, cfg_se_k, a.se_lo, a.se_hi); cta_sync();
+                se_pass<true>(MB, MA, g, cfg_se_k, a.se_lo, a.se_hi); cta_sync();
+                se_pass<true>(MA, MB, g, cfg_se_k, a.se_lo, a.se_hi); cta_sync();
+                se_pass<false>(MB, MA, g, cfg_se_k, a.se_lo, a.se_hi); cta_sync();
             }
             pt.tick();   // 5 close/open
             // ---- P5: hole fill ----------------------------------------------------
-            for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
-            cta_sync();
-            int R = ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
-            n_runs_max = max(n_runs_max, R);
-            ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
-            cta_sync();
+            unsigned* rowinfo = reinterpret_cast<unsigned*>(ws_s.row_first());
+            RowScan rs = mask_row_scan(cta, MA, g, rowinfo);
+            if (rs.any_multi) {                              // a row with several runs: the background may have holes
+                for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
+                cta_sync();
+                int R = ccl_build(cta, MB, g, false, true, ws_s, ws_g, ws, &pt);
+                n_runs_max = max(n_runs_max, R);
+                ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
+                cta_sync();
+                if (mode == MODE_FULL) rs = mask_row_scan(cta, MA, g, rowinfo);
+            }
             pt.tick();   // 6 hole fill
             if (mode == MODE_FULL) {
                 // ---- P6: largest 8-component centroid, shift ---------------------
-                R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws, &pt);
-                n_runs_max = max(n_runs_max, R);
                 unsigned area; unsigned long long sx, sy;
-                int broot = ccl_largest(sh.cs, g, ws, R, area, sx, sy);
+                int broot = 1;
+                if (rs.solid) { area = rs.area; sx = rs.sx; sy = rs.sy; }
+                else {
+                    const int R = ccl_build(cta, MA, g, true, false, ws_s, ws_g, ws, &pt);
+                    n_runs_max = max(n_runs_max, R);
+                    broot = ccl_largest(cta, g, ws, R, area, sx, sy);
+                }
                 if (broot != 0 && area > 0) {
                     cx = __ddiv_rn((double)sx, (double)area);
                     cy = __ddiv_rn((double)sy, (double)area);
@@ -343,9 +396,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
                 if (a.n_excl > 0) { apply_exclusions(MA, g, a.excl, a.n_excl, dx, dy); cta_sync(); }
             }
             // ---- P8: seg mask out -------------------------------------------------
-            seg_area = cta_popcount(sh.cs, MA, g);
-            if (a.seg_stats) mask_sums(sh.cs, MA, g, a.seg_stats + (long long)uid * 3);     // CSV export's mask_stats, optional
+            seg_area = cta_popcount(cta, MA, g);
+            if (cfg_seg_stats) mask_sums(cta, MA, g, cfg_seg_stats + (long long)uid * 3);     // CSV export's mask_stats, optional
             if (seg_out) store_mask_bytes(MA, g, seg_out);
+            if (cfg_seg_bits) store_mask_words(MA, g, bits_at(cfg_seg_bits));
             pt.tick();   // 8 exclusions + seg mask out
             if (mode == MODE_SEG_ONLY) {
                 write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, 0, 0, 0, cx, cy, 0, n_runs_max);
@@ -361,14 +415,14 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     if (mode == MODE_FILL) {
         for (int i = tid; i < g.nwords; i += kThreads) MB[i] = ~MA[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
         cta_sync();
-        ccl_build(sh.cs, MB, g, false, true, ws_s, ws_g, ws, &pt);
+        ccl_build(cta, MB, g, false, true, ws_s, ws_g, ws, &pt);
         ccl_paint(MA, MA, g, ws, [](int root) { return root != 0; });
         cta_sync();
         store_mask_bytes(MA, g, seg_out);
         return;
     }
     if (mode == MODE_STATS) {
-        mask_sums(sh.cs, MA, g, stats);
+        mask_sums(cta, MA, g, stats);
         return;
     }
     if (mode == MODE_ERODE) {
@@ -378,10 +432,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         return;
     }
     if (mode == MODE_LABEL) {
-        int R = ccl_build(sh.cs, MA, g, true, false, ws_s, ws_g, ws, &pt);
+        int R = ccl_build(cta, MA, g, true, false, ws_s, ws_g, ws, &pt);
         unsigned area; unsigned long long sx, sy;
-        int broot = ccl_largest(sh.cs, g, ws, R, area, sx, sy);
-        int nlab = ccl_rank_roots(sh.cs, ws, R);
+        int broot = ccl_largest(cta, g, ws, R, area, sx, sy);
+        int nlab = ccl_rank_roots(cta, ws, R);
         if (lab_out) store_labels(g, ws, lab_out);
         if (tid == 0) {
             stats[0] = nlab; stats[1] = broot ? (long long)ws.acc1()[broot] : 0; stats[2] = area;
@@ -389,7 +443,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         }
         return;
     }
-    if (mode == MODE_DETECT) seg_area = cta_popcount(sh.cs, MA, g);
+    if (mode == MODE_DETECT) seg_area = cta_popcount(cta, MA, g);
 
     // =========================== detector ======================================
     // ---- P9: square erosion ---------------------------------------------------
@@ -397,30 +451,43 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     if (a.p.erode_px > 0) X = erode_square_bits(MA, MB, MC, g, a.p.erode_px);
     pt.tick();   // 9 erosion
     // ---- P10: largest 8-component = ROI ---------------------------------------
-    int R = ccl_build(sh.cs, X, g, true, false, ws_s, ws_g, ws, &pt);
-    n_runs_max = max(n_runs_max, R);
-    unsigned roi_area; unsigned long long rsx, rsy;
-    const int broot = ccl_largest(sh.cs, g, ws, R, roi_area, rsx, rsy);
-    if (lab_out) {
-        ccl_rank_roots(sh.cs, ws, R);
-        store_labels(g, ws, lab_out);
+    unsigned roi_area = 0;
+    {
+        RowScan rs;
+        rs.solid = false;
+        if (!lab_out) rs = mask_row_scan(cta, X, g, reinterpret_cast<unsigned*>(ws_s.row_first()));
+        if (rs.solid) {                                      // one solid blob: it is the ROI
+            roi_area = rs.area;
+            for (int i = tid; i < g.nwords; i += kThreads) MD[i] = X[i];
+        } else {
+            const int R = ccl_build(cta, X, g, true, false, ws_s, ws_g, ws, &pt);
+            n_runs_max = max(n_runs_max, R);
+            unsigned long long rsx, rsy;
+            const int broot = ccl_largest(cta, g, ws, R, roi_area, rsx, rsy);
+            if (lab_out) {
+                ccl_rank_roots(cta, ws, R);
+                store_labels(g, ws, lab_out);
+            }
+            if (broot == 0 || roi_area == 0) {
+                if (def_out) zero_bytes(def_out, npix);
+                if (cfg_def_bits) zero_words(bits_at(cfg_def_bits), g.nwords);
+                write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, VI_STATUS_ROI_EMPTY, dx, dy, cx, cy, 0, n_runs_max);
+                return;
+            }
+            ccl_paint(MD, nullptr, g, ws, [broot](int root) { return root == broot; });
+        }
     }
-    if (broot == 0 || roi_area == 0) {
-        if (def_out) zero_bytes(def_out, npix);
-        write_record(a, uid, img, unit, otsu_t, seg_area, 0, 0, 0, VI_STATUS_ROI_EMPTY, dx, dy, cx, cy, 0, n_runs_max);
-        return;
-    }
-    ccl_paint(MD, nullptr, g, ws, [broot](int root) { return root == broot; });
     cta_sync();
     pt.tick();   // 10 ROI labelling
     const int thr = a.p.threshold;
     int n_amb = 0;
     int any_resid = 0;
-    if (a.p.defect_method == 1) {
+    int R = 0;
+    if (cfg_defect_method == 1) {
         // ---- P11': Canny edges inside the ROI (indexing_ui.py:1536-1539) ----------------
         canny_candidates(gray, g, a.canny_low, a.canny_high, MA, MB);
         cta_sync();
-        R = canny_hysteresis(sh.cs, MA, MB, MC, g, ws_s, ws_g, ws);
+        R = canny_hysteresis(cta, MA, MB, MC, g, ws_s, ws_g, ws);
         n_runs_max = max(n_runs_max, R);
         for (int i = tid; i < g.nwords; i += kThreads) { const unsigned v = MC[i] & MD[i]; MB[i] = v; any_resid |= (v != 0); }
         any_resid = cta_sync_or(any_resid);
@@ -429,9 +496,15 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     // ---- P11: median residual (second part: the dirty cells against the ROI) ------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
     cta_sync();
-    if (g.w <= kRankMaxW && rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes) {
+    if (SPEC || (g.w <= kRankMaxW && rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes)) {
         RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
         n_amb = rank_finish(gray, g, rw, thr, MD, MC, pt);
+        if (SPEC) {
+            // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
+            const int nuid = uid + (int)gridDim.x;
+            if (nuid < a.n_images * a.n_units)
+                cta.gpending = gather_issue(a, nuid, smem, plan.gray_bytes + plan.mask_bytes, &sh.gather_mbar) ? 1 : 0;
+        }
     } else {
         // units wider than the column-per-thread pass: exact rank count for every ROI pixel
         for (int i = tid; i < g.nwords; i += kThreads) {
@@ -448,27 +521,29 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     }
     pt.tick();   // 11 dirty cells + exact counts
     // ---- P12: open with the 3x3 cross -----------------------------------------
-    cross3_pass<true>(MC, MA, g); cta_sync();
-    cross3_pass<false>(MA, MB, g);
-    for (int i = tid; i < g.nwords; i += kThreads) any_resid |= (MA[i] != 0);       // erosion result non-empty <=> opening non-empty
+    // (MD, the ROI, is free again; MA may already be receiving the next unit's rows)
+    cross3_pass<true>(MC, MD, g); cta_sync();
+    cross3_pass<false>(MD, MB, g);
+    for (int i = tid; i < g.nwords; i += kThreads) any_resid |= (MD[i] != 0);       // erosion result non-empty <=> opening non-empty
     any_resid = cta_sync_or(any_resid);
     pt.tick();   // 12 open
     }
     if (!any_resid) {
         // nothing survives the opening: the detector returns None (indexing_ui.py:1559-1560)
         if (def_out) zero_bytes(def_out, npix);
+        if (cfg_def_bits) zero_words(bits_at(cfg_def_bits), g.nwords);
         write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, 0, 0, VI_STATUS_OK, dx, dy, cx, cy, n_amb, n_runs_max);
         return;
     }
     // ---- P13: hole fill + per-component contour area filter ---------------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = ~MB[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
     cta_sync();
-    R = ccl_build(sh.cs, MC, g, false, true, ws_s, ws_g, ws, &pt);
+    R = ccl_build(cta, MC, g, false, true, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     ccl_paint(MB, MB, g, ws, [](int root) { return root != 0; });
     cta_sync();
     pt.tick();   // 13 defect hole fill
-    R = ccl_build(sh.cs, MB, g, true, false, ws_s, ws_g, ws, &pt);
+    R = ccl_build(cta, MB, g, true, false, ws_s, ws_g, ws, &pt);
     n_runs_max = max(n_runs_max, R);
     {
         const int Rpad = (R + kThreads - 1) / kThreads * kThreads;
@@ -492,20 +567,21 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     unsigned long long kept = 0;
     for (int i = 1 + tid; i <= R; i += kThreads)
         if (ws.parent()[i] == i && keep(i)) ++kept;
-    const int n_kept = (int)cta_sum_u64(sh.cs, kept);
+    const int n_kept = (int)cta_sum_u64(cta, kept);
     ccl_paint(ME, nullptr, g, ws, keep);
     cta_sync();
     pt.tick();   // 14 component area filter
     // ---- P14: verdict ---------------------------------------------------------
-    const unsigned defect_area = cta_popcount(sh.cs, ME, g);
+    const unsigned defect_area = cta_popcount(cta, ME, g);
     if (def_out) store_mask_bytes_sparse(ME, g, def_out);
+    if (cfg_def_bits) store_mask_words(ME, g, bits_at(cfg_def_bits));
     const int status = (n_kept > 0 && (long long)defect_area >= min_area) ? VI_STATUS_NG : VI_STATUS_OK;
     write_record(a, uid, img, unit, otsu_t, seg_area, roi_area, n_kept > 0 ? defect_area : 0u, n_kept, status, dx, dy,
                  cx, cy, n_amb, n_runs_max);
     pt.tick();   // 15 defect mask out + record
 }
 
-template <bool PROF>
+template <bool PROF, bool SPEC, bool GMEM>
 __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ UnitShared sh_raw;
@@ -518,8 +594,15 @@ __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_const
     __builtin_assume(__isShared(shp));
     UnitShared& sh = *shp;
     const int n_total = a.n_images * a.n_units;
+    Cta cta;
+    cta.s = &sh.cs; cta.par = 0u; cta.gpar = 0u; cta.gpending = 0;
+    if (SPEC) {
+        if (threadIdx.x == 0) mbar_init(&sh.gather_mbar, 1u);
+        cta_sync();
+    }
+    unsigned char* base = GMEM ? a.arena + (long long)blockIdx.x * a.arena_stride : smem;
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
-        process_unit<PROF>(a, uid, smem, sh);
+        process_unit<PROF, SPEC, GMEM>(a, uid, base, smem, sh, cta);
         cta_sync();
     }
 }
