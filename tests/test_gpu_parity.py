@@ -541,6 +541,35 @@ def test_unit_size_bound_is_documented_and_loud(insp):
     assert e.value.code == -4 and "bound" in str(e.value)
 
 
+def test_config5_full_size_against_the_oracle(insp):
+    """BASELINE configs[4] as stated: one 16384x12000 frame, 11,904 units of 96x96 on a 128-pixel lattice, salt noise in
+    the plates, threshold 8 / min-area 0 / erode 1 (hundreds of components per unit).  Every record and every mask of
+    every unit against the cv2 oracle."""
+    import torch
+    boxes = synth.dense_grid_boxes()
+    assert len(boxes) == 11904
+    fr = synth.make_frame(5, boxes, H=12000, W=16384, inset=8, salt_p=0.02)
+    p = vi_b200.default_params(threshold=8, min_area=0, erode_px=1)
+    bx = [(b, i) for i, b in enumerate(boxes)]
+    insp.configure(Grid(boxes=bx), is_reference=True)
+    rec, seg, dfm = insp.inspect_batch(torch.from_numpy(fr[None]).cuda(), p)
+    torch.cuda.synchronize()
+    rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+    segs = insp.split_masks(seg.cpu().numpy())
+    defs = insp.split_masks(dfm.cpu().numpy())
+    recs, osegs, odefs = R.inspect_frame(fr, bx, R.Params(threshold=8, min_area=0, erode_px=1), (), None, True)
+    n_kept = 0
+    for i in range(len(boxes)):
+        assert np.array_equal(segs[i], osegs[i]), (i, 'seg')
+        want = odefs[i] if odefs[i] is not None else np.zeros_like(defs[i])
+        assert np.array_equal(defs[i], want), (i, 'defect', int((defs[i] != want).sum()))
+        for k in ('status', 'defect_area', 'seg_area', 'roi_area', 'n_kept', 'dx', 'dy'):
+            assert rec[i][k] == recs[i][k], (i, k, rec[i][k], recs[i][k])
+        assert rec[i]['cx'] == recs[i]['cx'] and rec[i]['cy'] == recs[i]['cy']
+        n_kept += int(rec[i]['n_kept'])
+    assert n_kept > 50 * len(boxes)                       # the stress is real: many components per unit
+
+
 def test_full_size_batch_properties(insp, golden):
     """BASELINE configs[1] at its full size (64 frames of 4096x3000, 3,072 units) through size-independent
     properties: the golden frame's units match the reference's outputs wherever the frame sits in the batch; copies of

@@ -258,6 +258,61 @@ VI_PHASE RowScan mask_row_scan(Cta& cs, const unsigned* M, const Geom& g, unsign
     return r;
 }
 
+// Hole fill without labelling.  The background that is 4-connected to the crop border is grown directly on the bit
+// rows: one thread owns one row and, per round, seeds it with what is already reached in the row itself and in the
+// rows above and below, then extends every seed to the ends of its background run (an addition ripples a carry
+// through a run of ones: left to right on the words, right to left on their bit reversals).  A round crosses any
+// number of pixels horizontally and one row vertically; round 0 seeds the runs that touch the row's ends and the
+// whole first / last row.  Reads of neighbour rows may see a round's old or new words -- both are subsets of the true
+// reachable set, so the iteration is monotone and its fixed point is exact.  A plate with inclusions converges at
+// once; if `kFloodRounds` do not suffice (spirals, long vertical channels) the caller labels the background instead.
+//   M: the mask (foreground);  R: scratch, receives the reached background;  returns true when converged, and then
+//   M | holes == ~R & row mask.
+constexpr int kFloodRounds = 5;
+
+VI_PHASE bool flood_border_background(const unsigned* M, unsigned* R, const Geom& g) {
+    const unsigned lastbit = 1u << ((g.w - 1) & 31);
+    for (int round = 0; round <= kFloodRounds; ++round) {
+        int changed = 0;
+        for (int y = threadIdx.x; y < g.h; y += kThreads) {
+            const unsigned* mrow = M + y * g.wpr;
+            unsigned* rrow = R + y * g.wpr;
+            const unsigned* up = R + max(y - 1, 0) * g.wpr;
+            const unsigned* dn = R + min(y + 1, g.h - 1) * g.wpr;
+            const bool edge_row = y == 0 || y == g.h - 1;
+            // left to right: seeds and their extension towards higher x
+            unsigned carry = 0, diff = 0;
+            for (int c = 0; c < g.wpr; ++c) {
+                const unsigned b = ~mrow[c] & row_mask_of(g, c);
+                unsigned s;
+                if (round == 0) s = edge_row ? b : ((c == 0 ? 1u : 0u) | (c == g.wpr - 1 ? lastbit : 0u));
+                else s = rrow[c] | up[c] | dn[c];
+                s = (s | carry) & b;
+                const unsigned sum = b + s;
+                carry = sum < b ? 1u : 0u;                     // the run reaches bit 31: it goes on in the next word
+                const unsigned v = ((sum ^ b) & b) | s;
+                if (round != 0) diff |= v ^ rrow[c];
+                rrow[c] = v;
+            }
+            // right to left: extension towards lower x
+            carry = 0;
+            for (int c = g.wpr - 1; c >= 0; --c) {
+                const unsigned b = __brev(~mrow[c] & row_mask_of(g, c));
+                const unsigned old = rrow[c];
+                const unsigned s = (__brev(old) | carry) & b;
+                const unsigned sum = b + s;
+                carry = sum < b ? 1u : 0u;
+                const unsigned v = old | __brev((sum ^ b) & b);
+                diff |= v ^ old;
+                rrow[c] = v;
+            }
+            changed |= diff != 0u;
+        }
+        if (!cta_sync_or(round == 0 ? 1 : changed)) return true;
+    }
+    return false;
+}
+
 // Warp-aggregated per-root accumulation: lanes whose root equals the first valid
 // lane's root are reduced with REDUX and added once; the rest add individually.
 __device__ __forceinline__ void agg_add(unsigned* acc, bool valid, int root, unsigned val) {
