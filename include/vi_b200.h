@@ -221,6 +221,9 @@ int vi_detect_defects(vi_ctx* ctx, const uint8_t* gray, const uint8_t* seg_mask,
 /* Per-phase SM cycle counts of every unit of subsequent vi_inspect_batch calls:
  * d_cycles is device memory, [n_images*n_units][40] int64 (NULL switches it off). */
 int vi_debug_set_profile(vi_ctx* ctx, long long* d_cycles);
+/* Self-checked build (libvi_b200_checked.so, -DVI_CHECKED=1): the first bounds check that failed in any kernel since the
+ * library was loaded (0 = none; codes: vi_device.cuh CheckCode).  The production library returns VI_ERR_UNSUPPORTED. */
+int vi_debug_check_word(vi_ctx* ctx, uint32_t* out_code);
 /* Compares the reciprocal-based division of the Otsu recurrence with the IEEE divide on
  * n_samples pseudo-random operand pairs; *mismatches must come back 0. */
 int vi_debug_fastdiv_check(vi_ctx* ctx, long long n_samples, unsigned long long seed, long long* mismatches);

@@ -567,7 +567,28 @@ def test_config5_full_size_against_the_oracle(insp):
             assert rec[i][k] == recs[i][k], (i, k, rec[i][k], recs[i][k])
         assert rec[i]['cx'] == recs[i]['cx'] and rec[i]['cy'] == recs[i]['cy']
         n_kept += int(rec[i]['n_kept'])
-    assert n_kept > 50 * len(boxes)                       # the stress is real: many components per unit
+    assert n_kept > 4 * len(boxes)                        # several kept components per unit (the 3x3 opening removes lone salt pixels)
+
+
+def test_checked_build_over_adversarial_inputs():
+    """The same sources built with -DVI_CHECKED=1 (bounds asserts on the threshold band's list, the run tables and their
+    shared / global choice, union-find parents, the dirty-cell and ambiguous-pixel lists, lattice slots, histogram
+    counters) over the adversarial masks, noise crops, the default-configuration batch and dense small units: no check
+    may fire.  Stands in for compute-sanitizer, which the GPU pool refuses."""
+    import subprocess
+    import sys
+    from vi_b200 import _build
+    _build.build(force=False, checked=True)
+    env = dict(os.environ, VI_B200_LIB="checked")
+    res = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "checked_run.py")], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "check_word 0" in res.stdout, res.stdout[-2000:]
+    # and the production library says so when asked for a check word
+    import ctypes as C
+    insp = vi_b200.Inspector(0)
+    w = C.c_uint32(0)
+    assert insp._lib.vi_debug_check_word(insp._ctx, C.byref(w)) == -3
 
 
 def test_full_size_batch_properties(insp, golden):

@@ -96,3 +96,79 @@ def test_exclusion_table():
     rows = G.exclusions_to_table([{'shape': 'rect', 'x': 1, 'y': 2, 'w': 3, 'h': 4}, {'shape': 'circle', 'cx': 5, 'cy': 6, 'r': 7},
                                   {'shape': 'blob', 'cx': 1}, {'shape': 'rect', 'x': 'oops'}])
     assert rows == [(0, 1, 2, 3, 4), (1, 5, 6, 7, 0), (1, 1, 0, 0, 0)]
+
+
+class _FakeBits(bytearray):
+    """Stands in for the sip.voidptr QImage.bits() returns: a buffer with setsize()."""
+    def setsize(self, n):
+        assert n == len(self)
+
+
+class _FakeQImage:
+    class Format:
+        Format_ARGB32 = 5
+
+    def __init__(self, bgra):
+        self._a = np.ascontiguousarray(bgra, np.uint8)
+
+    def convertToFormat(self, fmt):
+        assert fmt == _FakeQImage.Format.Format_ARGB32
+        return self
+
+    def bits(self):
+        return _FakeBits(self._a.tobytes())
+
+    def sizeInBytes(self):
+        return self._a.size
+
+    def height(self):
+        return self._a.shape[0]
+
+    def width(self):
+        return self._a.shape[1]
+
+
+def test_qimage_to_gray_array_on_colour_input(monkeypatch):
+    """The drop-in's qimage_to_gray_array (a numpy formula) against the reference's own function
+    (segmentation.py:10-24: reversed channels into cv2.cvtColor(BGR2GRAY)) on colour pixels, driven through a
+    numpy-backed QImage stand-in; and against cv2 directly, so the check also runs where /root/reference is absent."""
+    import importlib.util
+    cv2 = pytest.importorskip("cv2")
+    from vi_b200 import segmentation as seg
+    rng = np.random.default_rng(3)
+    bgra = rng.integers(0, 256, size=(37, 53, 4), dtype=np.uint8)
+    bgra[:8, :, 0] = bgra[:8, :, 1] = bgra[:8, :, 2] = np.arange(53, dtype=np.uint8)[None, :] * 4      # a mono strip: identity
+    monkeypatch.setattr(seg, "QImage", _FakeQImage)
+    got = seg.qimage_to_gray_array(_FakeQImage(bgra))
+    want = cv2.cvtColor(np.ascontiguousarray(bgra[:, :, :3][:, :, ::-1]), cv2.COLOR_BGR2GRAY)
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    assert np.array_equal(got[:8], bgra[:8, :, 0])
+    ref_path = "/root/reference/segmentation.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_segmentation", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        monkeypatch.setattr(ref, "QImage", _FakeQImage)
+        assert np.array_equal(got, ref.qimage_to_gray_array(_FakeQImage(bgra)))
+    monkeypatch.setattr(seg, "QImage", None)
+    with pytest.raises(RuntimeError):
+        seg.qimage_to_gray_array(_FakeQImage(bgra))
+
+
+def test_packed_mask_png_round_trip(tmp_path):
+    """The kernel's packed-bit mask layout (rows of 32-bit words, PNG bit order) written as a 1-bit PNG reads back as
+    the 0/255 mask: the consumer contract of export_masks_and_csv (indexing_ui.py:2703-2722) on packed output."""
+    cv2 = pytest.importorskip("cv2")
+    from vi_b200 import export
+    rng = np.random.default_rng(2)
+    for (h, w) in ((315, 316), (17, 33), (5, 8), (40, 1)):
+        mask = (rng.random((h, w)) < 0.4).astype(np.uint8) * 255
+        wpr = (w + 31) // 32
+        bits = np.zeros((h, wpr * 32), np.uint8)
+        bits[:, :w] = mask > 0
+        packed = np.packbits(bits, axis=1)                   # big bit order within bytes = VI_MASKS_PACKED
+        assert packed.shape == (h, wpr * 4)
+        fn = str(tmp_path / f"m_{h}_{w}.png")
+        export.write_mask_png(fn, packed, w, h)
+        back = cv2.imread(fn, cv2.IMREAD_GRAYSCALE)
+        assert back is not None and back.shape == (h, w) and np.array_equal(back, mask)

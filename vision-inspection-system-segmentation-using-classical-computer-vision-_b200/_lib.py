@@ -38,7 +38,7 @@ EXPORTS = [
     "vi_inspect_batch_host", "vi_inspect_batch_host_fmt", "vi_set_packed_mask_output", "vi_packed_mask_bytes",
     "vi_packed_mask_offsets", "vi_host_upload_bytes", "vi_peer_table_create", "vi_peer_table_open", "vi_peer_table_close",
     "vi_peer_table_destroy", "vi_peer_table_read", "vi_set_record_peers", "vi_segment_cell", "vi_fill_internal_holes", "vi_mask_stats", "vi_erode_square",
-    "vi_label_components", "vi_detect_defects", "vi_ingest_argb32", "vi_ingest_gray16", "vi_set_seg_stats_output", "vi_debug_set_profile", "vi_debug_fastdiv_check", "vi_debug_adaptive_taps",
+    "vi_label_components", "vi_detect_defects", "vi_ingest_argb32", "vi_ingest_gray16", "vi_set_seg_stats_output", "vi_debug_set_profile", "vi_debug_check_word", "vi_debug_fastdiv_check", "vi_debug_adaptive_taps",
 ]
 
 _lib = None
@@ -55,7 +55,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    # VI_B200_LIB=checked selects the self-checked build of the same sources (vi_debug_check_word)
+    path = _build.CHECKED_LIB_PATH if os.environ.get("VI_B200_LIB") == "checked" else _build.LIB_PATH
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the CUDA extension is the product; there is no CPU fallback)")
@@ -96,6 +97,7 @@ def load():
     lib.vi_erode_square.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     lib.vi_label_components.argtypes = [vp, vp, C.c_int, C.c_int, vp, P(i32), P(i32), P(i64), P(i64), P(i64)]
     lib.vi_debug_set_profile.argtypes = [vp, vp]
+    lib.vi_debug_check_word.argtypes = [vp, P(C.c_uint32)]
     lib.vi_debug_fastdiv_check.argtypes = [vp, i64, C.c_uint64, P(i64)]
     lib.vi_detect_defects.argtypes = [vp, vp, vp, C.c_int, C.c_int, P(ViParams), vp, P(i32), vp]
     lib.vi_debug_adaptive_taps.argtypes = [C.c_int, vp]

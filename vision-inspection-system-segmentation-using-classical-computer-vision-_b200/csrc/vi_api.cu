@@ -328,6 +328,21 @@ extern "C" int vi_debug_fastdiv_check(vi_ctx* c, long long n_samples, unsigned l
     return VI_OK;
 }
 
+extern "C" int vi_debug_check_word(vi_ctx* c, uint32_t* out) {
+    if (!c || !out) return fail(VI_ERR_ARG, "vi_debug_check_word: null");
+#ifdef VI_CHECKED
+    VI_DEVICE(c);
+    CU(cudaDeviceSynchronize());
+    unsigned w = 0;
+    CU(cudaMemcpyFromSymbol(&w, vi::g_vi_check_word, sizeof w));
+    *out = w;
+    return VI_OK;
+#else
+    *out = 0;
+    return fail(VI_ERR_UNSUPPORTED, "vi_debug_check_word: this library was built without VI_CHECKED");
+#endif
+}
+
 extern "C" int vi_debug_set_profile(vi_ctx* c, long long* d_cycles) {
     if (!c) return fail(VI_ERR_ARG, "ctx is null");
     c->prof = d_cycles;
@@ -595,7 +610,9 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
         const int lim = c->smem_optin - c->smem_static;
         CU(cudaFuncSetAttribute(vi_unit_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         CU(cudaFuncSetAttribute(vi_unit_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+#ifndef VI_CHECKED
         CU(cudaFuncSetAttribute(vi_unit_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+#endif
         CU(cudaFuncSetAttribute(vi_unit_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         c->smem_set = lim;
     }
@@ -613,8 +630,11 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
                 (a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0 &&
                 gs.wmax <= kRankMaxW && rank_ws_bytes(gs.wmax) + kOtsuWsBytes <= gs.plan.ws_bytes && gs.plan.n_hist >= kWarps / 2;
     if (spec) { const char* e = getenv("VI_KERNEL"); if (e && strcmp(e, "general") == 0) spec = false; }
+#ifndef VI_CHECKED
     if (a.prof && spec) vi_unit_kernel<true, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);   // diagnostics build: phase timers
-    else if (spec) vi_unit_kernel<false, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);
+    else
+#endif
+    if (spec) vi_unit_kernel<false, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);
     else { a.prof = nullptr; vi_unit_kernel<false, false, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a); }
     CU(cudaGetLastError());
     return VI_OK;

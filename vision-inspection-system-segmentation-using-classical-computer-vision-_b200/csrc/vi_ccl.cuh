@@ -68,6 +68,7 @@ __device__ inline void ccl_jump(int* parent, int R) {
         int changed = 0;
         for (int i = 1 + threadIdx.x; i <= R; i += kThreads) {
             const int p = parent[i];
+            VI_CHECK(p >= 0 && p <= R, CHK_UF_PARENT);
             int q = parent[p];
             q = parent[q];
             q = parent[q];
@@ -107,6 +108,7 @@ VI_PHASE int ccl_build(Cta& cs, const unsigned* M, const Geom& g, bool conn8, bo
     cta_excl_scan2(cs, os, oe, R, Re);
     if (pt) pt->acc(23);
     ws = ((int)R <= ws_s.cap) ? ws_s : ws_g;
+    VI_CHECK((int)R <= ws.cap && R == Re, CHK_RUN_CAP);            // every start has its end; the global table holds any mask
     for (int i = i0; i < i1; ++i) {
         int y, c; word_rc(g, i, y, c);
         unsigned s, e;
@@ -115,12 +117,14 @@ VI_PHASE int ccl_build(Cta& cs, const unsigned* M, const Geom& g, bool conn8, bo
         while (s) {
             int b = __ffs(s) - 1; s &= s - 1;
             ++os;
+            VI_CHECK(os >= 1 && os <= R, CHK_RUN_INDEX);
             ws.xs()[os] = (unsigned short)(c * 32 + b);
             ws.yy()[os] = (unsigned short)y;
         }
         while (e) {
             int b = __ffs(e) - 1; e &= e - 1;
             ++oe;
+            VI_CHECK(oe >= 1 && oe <= R, CHK_RUN_INDEX);
             ws.xe()[oe] = (unsigned short)(c * 32 + b);
         }
     }
@@ -173,6 +177,7 @@ VI_PHASE int ccl_build(Cta& cs, const unsigned* M, const Geom& g, bool conn8, bo
                 if ((int)ws.xe()[mid] < xs - c8) lo = mid + 1; else hi = mid;
             }
             if (lo < j1 && (int)ws.xs()[lo] <= xe + c8) link = lo;
+            VI_CHECK(j0 >= 1 && j0 <= j1 && j1 <= i, CHK_ROW_TABLE);
         }
         ws.parent()[i] = link;
         ws.acc0()[i] = 0;
@@ -343,6 +348,7 @@ VI_PHASE void ccl_paint(unsigned* dst, const unsigned* base, const Geom& g, cons
         int y, c; word_rc(g, i, y, c);
         int x0 = c * 32, x1 = x0 + 31;
         int j0 = ws.row_first()[y], j1 = ws.row_first()[y + 1];
+        VI_CHECK(j0 >= 1 && j0 <= j1 && j1 <= ws.cap + 1, CHK_PAINT_RUN);
         int lo = j0, hi = j1;                 // first run with xe >= x0
         while (lo < hi) {
             int mid = (lo + hi) >> 1;

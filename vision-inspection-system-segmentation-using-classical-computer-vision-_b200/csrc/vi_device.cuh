@@ -12,6 +12,26 @@
 
 namespace vi {
 
+// Self-checks (the pool's compute-sanitizer is closed): a build with -DVI_CHECKED=1 (libvi_b200_checked.so,
+// vi_b200/_build.py) asserts the bounds of every list and table that has a capacity -- the uncertain-pixel list of the
+// threshold band, the run tables and the choice between the shared and the global one, union-find parents, the
+// dirty-cell and ambiguous-pixel lists and the lattice rows of the median stage, the byte counters of the histogram --
+// and records the first failure in a device word that vi_debug_check_word returns (0 = none).  The production build
+// compiles them away.  tests/test_gpu_parity.py::test_checked_build_over_adversarial_inputs runs it.
+#ifdef VI_CHECKED
+__device__ unsigned g_vi_check_word = 0;
+#define VI_CHECK(cond, code)                                                          \
+    do {                                                                              \
+        if (!(cond)) atomicCAS(&::vi::g_vi_check_word, 0u, (unsigned)(code));         \
+    } while (0)
+#else
+#define VI_CHECK(cond, code) do { } while (0)
+#endif
+enum CheckCode : unsigned {
+    CHK_BAND_LIST = 1, CHK_RUN_INDEX = 2, CHK_RUN_CAP = 3, CHK_UF_PARENT = 4, CHK_DIRTY_LIST = 5, CHK_EXACT_LIST = 6,
+    CHK_LATTICE_SLOT = 7, CHK_HIST_COUNTER = 8, CHK_ROW_TABLE = 9, CHK_PAINT_RUN = 10, CHK_GATHER_STAGE = 11,
+};
+
 // Pipeline phases.  (Compiling them as __noinline__ functions of their own was measured: reference
 // arguments then live in local memory and the labelling phases ran 2-3x slower.)
 #define VI_PHASE __device__ inline

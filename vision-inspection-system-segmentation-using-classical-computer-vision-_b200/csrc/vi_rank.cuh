@@ -59,6 +59,7 @@ struct RankWs {
     int exact_cap;
     int* counters;      // shared: [0] dirty cells, [1] ambiguous pixels listed, [2] ambiguous pixels total
     int P, cpitch;
+    int dirty_cap;      // cells of the largest unit: what the dirty list holds
 };
 
 // Columns per lane of the prefix pass (odd: a lane's chunk starts land on distinct banks) and the row pitch of
@@ -91,6 +92,7 @@ __device__ inline RankWs rank_ws_carve(unsigned char* base, int w, unsigned char
     r.dirty = reinterpret_cast<uint2*>(lists);
     r.exact = reinterpret_cast<unsigned*>(lists + (long long)((wmax + kCell - 1) / kCell) * ((hmax + kCell - 1) / kCell) * 8);
     r.exact_cap = kExactCap;
+    r.dirty_cap = ((wmax + kCell - 1) / kCell) * ((hmax + kCell - 1) / kCell);
     return r;
 }
 
@@ -168,6 +170,7 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
             } else if (!(gv >= u2 && gv <= u3)) {
                 atomicAdd(&w.counters[2], 1);
                 const int k = atomicAdd(&w.counters[1], 1);
+                VI_CHECK(k >= 0 && y < g.h && x < g.w, CHK_EXACT_LIST);
                 if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | (unsigned)x;
                 else if (rank_exact_pixel_thread(gray, g, thr, x, y)) atomicOr(&CAND[wi], bit);
             }
@@ -219,6 +222,7 @@ __device__ __forceinline__ void rank_group_cells(const Geom& g, RankWs& w, const
             int base = 0;
             if (lane == 0) base = atomicAdd(&w.counters[0], __popc(dm));
             base = __shfl_sync(kFull, base, 0);
+            VI_CHECK(base >= 0 && base + __popc(dm) <= w.dirty_cap, CHK_DIRTY_LIST);
             if (dirty) w.dirty[base + __popc(dm & ((1u << lane) - 1u))] = make_uint2(((unsigned)cj << 16) | (unsigned)i, cw);
         }
         if (m + 1 < kGrp) { C0 += cs[m + 7].x - cs[m].x; C1 += cs[m + 7].y - cs[m].y; }
@@ -341,6 +345,7 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
     asm volatile("" : "+r"(P), "+r"(cpitch), "+r"(gp));
     const int csx = vact ? 1 + vcol : P - 1;                  // column slot (dummy for lanes without a column)
     const int cmx = cell_lead ? vcell : cpitch - 1;           // cell slot (dummy for lanes that lead no cell)
+    VI_CHECK(csx >= 1 && csx < P && cmx >= 0 && cmx < cpitch && 1 + g.w <= P - 1 && nlx <= cpitch - 1, CHK_LATTICE_SLOT);
     OtsuJob job;
     const bool owarp = warp == kOtsuWarp;
     const bool oslice = owarp && !vwarp;                      // idle during V: the scan rides along
@@ -402,6 +407,7 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, int thr, 
     const int hm1 = g.h - 1, wm1 = g.w - 1;
     // ---- dirty cells: per-pixel classification ----------------------------------------
     const int nd = w.counters[0];
+    VI_CHECK(nd >= 0 && nd <= w.dirty_cap, CHK_DIRTY_LIST);
     for (int i = tid; i < nd; i += kThreads) {
         const uint2 e = w.dirty[i];
         rank_dirty_cell(gray, g, thr, ROI, CAND, w, (int)(e.x & 0xffffu), (int)(e.x >> 16), e.y);

@@ -28,3 +28,28 @@ def write_masks_summary_csv(path: str, rows: Iterable[dict]) -> None:
         writer.writeheader()
         for row in rows:
             writer.writerow(row)
+
+
+def write_mask_png(path: str, packed_rows, w: int, h: int) -> None:
+    """A unit's mask as a 1-bit grayscale PNG straight from the packed-bit output of the kernel (VI_MASKS_PACKED:
+    rows of 32-bit words, first pixel = most significant bit of its byte -- a PNG scanline of bit depth 1 is exactly
+    the first ceil(w / 8) bytes of such a row).  Decoders expand it to 0 / 255, so `mask_stats` of the re-read file
+    (export_masks_and_csv, indexing_ui.py:2703-2722) sees the same mask as from the reference's 8-bit `mask_%04d.png`."""
+    import struct
+    import zlib
+    rows = np.asarray(packed_rows, dtype=np.uint8).reshape(h, -1)
+    nb = (w + 7) // 8
+    if rows.shape[1] < nb:
+        raise ValueError(f"packed rows hold {rows.shape[1]} bytes, a {w}-pixel scanline needs {nb}")
+    raw = np.zeros((h, nb + 1), np.uint8)                   # filter type 0 in front of every scanline
+    raw[:, 1:] = rows[:, :nb]
+    if w % 8:
+        raw[:, nb] &= np.uint8((0xFF << (8 - w % 8)) & 0xFF)   # padding bits of the last byte are zero
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    with open(path, 'wb') as f:
+        f.write(b"\x89PNG\r\n\x1a\n")
+        f.write(chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 1, 0, 0, 0, 0)))
+        f.write(chunk(b"IDAT", zlib.compress(raw.tobytes(), 6)))
+        f.write(chunk(b"IEND", b""))
