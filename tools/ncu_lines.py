@@ -21,7 +21,7 @@ def main():
     seq, cur, inker = {}, None, False
     for ln in dis.split("\n"):
         if ln.startswith("//---") and ".text." in ln:
-            inker = "vi_unit_kernelILb0" in ln
+            inker = "vi_unit_kernelILb0ELb1ELb0E" in ln
             continue
         if not inker:
             continue
