@@ -628,7 +628,7 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
     bool spec = a.mode == MODE_FULL && a.blur_k == 3 && a.se_k == 3 && a.p.seg_method == 0 && a.p.defect_method == 0 &&
                 !a.labels_out && !a.seg_stats && !a.seg_bits && !a.def_bits && !a.aux_mask && !a.stats_out &&
                 (a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0 &&
-                gs.wmax <= kRankMaxW && rank_ws_bytes(gs.wmax) + kOtsuWsBytes <= gs.plan.ws_bytes && gs.plan.n_hist >= kWarps / 2;
+                rank_ws_bytes(gs.wmax, gs.hmax) + kOtsuWsBytes <= (long long)(kNumMasks - 1) * gs.plan.mask_bytes + gs.plan.ws_bytes && gs.plan.n_hist >= kWarps / 2;
     if (spec) { const char* e = getenv("VI_KERNEL"); if (e && strcmp(e, "general") == 0) spec = false; }
 #ifndef VI_CHECKED
     if (a.prof && spec) vi_unit_kernel<true, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);   // diagnostics build: phase timers

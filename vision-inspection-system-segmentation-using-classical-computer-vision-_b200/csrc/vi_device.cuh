@@ -46,7 +46,7 @@ constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch domain that exchange 
 constexpr int kMaxTaps = 33;
 constexpr int kMaxSE = 33;
 constexpr int kMaxAdapt = 201;      // widest adaptive-threshold block (the reference's widget range, indexing_ui.py:805)
-constexpr int kLevels = 6;         // rank-count levels of the median stage (two words of three 10-bit fields)
+constexpr int kLevels = 3;         // rank-count levels of the median stage (one word of three 10-bit fields)
 constexpr int kNumMasks = 5;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -91,6 +91,27 @@ __host__ __device__ inline Geom make_geom(int w, int h) {
     return g;
 }
 
+// Geometry of the median stage's lattice workspace (vi_rank.cuh), here because the plans below size it.
+constexpr int kCell = 3;
+constexpr int kColsPerWarp = 30;         // V pass: 10 whole cells per warp
+constexpr int kVPad = 3;                 // virtual cells either side of a lattice row (the window is 7 cells wide)
+constexpr int kGrp = 6;                  // cells per task of the C pass
+constexpr unsigned kFlag = 0x20080200u;  // bit 9 of each 10-bit field
+constexpr unsigned kGe263 = 249u | (249u << 10) | (249u << 20);   // field + 249 >= 512  <=>  field >= 263
+constexpr unsigned kGe179 = 333u | (333u << 10) | (333u << 20);   // field + 333 >= 512  <=>  field >= 179
+__host__ __device__ inline int rank_nlx(int w) { return (w + kCell - 1) / kCell; }
+__host__ __device__ inline int rank_ngrp(int w) { return (rank_nlx(w) + kGrp - 1) / kGrp; }
+// Row pitch of cs in words: every slot a C task can read (kGrp * ngrp + 6) and the V pass's dummy slot; odd, so the
+// rows that the lanes of a half-warp hold land on distinct banks.
+__host__ __device__ inline int rank_P(int w) { return ((rank_nlx(w) + 2 * kVPad > kGrp * rank_ngrp(w) + 6 ? rank_nlx(w) + 2 * kVPad : kGrp * rank_ngrp(w) + 6) + 1) | 1; }
+// cmm pitch: every cell a C task can read, half of it odd (same bank argument for 16-bit entries).
+__host__ __device__ inline int rank_cpitch(int w) { return 2 * ((kGrp * rank_ngrp(w) + 1) / 2 | 1); }
+__host__ __device__ inline long long rank_ws_bytes(int w, int h) {
+    const long long nly = (h + kCell - 1) / kCell;
+    return (((nly + 7) & ~7ll) * rank_P(w) * 4 + nly * rank_cpitch(w) * 2 + 64 + 15) & ~15ll;
+}
+
+
 // Shared-memory plan for the largest unit of a grid (host computes, kernel follows).
 struct SmemPlan {
     int gray_bytes;    // [0, gray_bytes): gray crop
@@ -111,12 +132,8 @@ __host__ inline bool make_plan(int wmax, int hmax, int smem_limit, int fixed, Sm
     p->gray_bytes = align16(gray_need > 0 ? gray_need : g.gp * hmax);
     p->mask_bytes = align16((mask_words_need > 0 ? mask_words_need : g.nwords) * 4);
     p->band_pitch = 0;
-    // rank-count stage workspace (vi_rank.cuh: rank_ws_bytes) for units it covers
-    int cpitch = ((wmax + 2) / 3 + 2) & ~1;
-    int rch = wmax <= 352 ? 11 : 15;
-    int band = wmax <= 480 ? 16 * (32 * rch + 3) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
     int otsu = 3 * 256 * 8 + 64;                // vi_pipeline.cuh: kOtsuWsBytes, at the end of the workspace
-    band += otsu;                               // the Otsu warp works next to the rank-count cell pass
+    int band = otsu;                            // (the median stage's lattice lives in the mask region: no claim here)
     int rowfirst = align16((hmax + 2) * 4);
     int want_cap = 2048;
     int ccl = rowfirst + (want_cap + 1) * 18 + 64;
@@ -156,16 +173,15 @@ __host__ inline bool make_plan_gmem(int wmax, int hmax, SmemPlan* p, int gray_ne
     p->gray_bytes = align16(gray_need > 0 ? gray_need : g.gp * hmax);
     p->mask_bytes = align16((mask_words_need > 0 ? mask_words_need : g.nwords) * 4);
     p->band_pitch = 0;
-    int cpitch = ((wmax + 2) / 3 + 2) & ~1;
-    int rch = wmax <= 352 ? 11 : 15;
-    int band = wmax <= 480 ? 16 * (32 * rch + 3) * 8 + 32 * cpitch * 2 + 64 * 4 : 0;   // vi_rank.cuh: rank_ws_bytes
     int otsu = 3 * 256 * 8 + 64;
     int rowfirst = align16((hmax + 2) * 4);
     int want_cap = 8192;
     int ccl = rowfirst + (want_cap + 1) * 18 + 64;
-    int ws = band + otsu;
-    if (ccl > ws) ws = ccl;
-    p->ws_bytes = align16(ws);
+    // the median stage's lattice (vi_rank.cuh) spans the masks after the first and this workspace
+    long long rank = rank_ws_bytes(wmax, hmax) + otsu - (long long)(kNumMasks - 1) * p->mask_bytes;
+    long long ws = rank > ccl ? rank : ccl;
+    if (ws > 0x7fff0000ll) return false;
+    p->ws_bytes = align16((int)ws);
     p->run_cap = (p->ws_bytes - rowfirst - 64) / 18 - 1;
     if (p->run_cap > 65534) p->run_cap = 65534;
     p->n_hist = kWarps;
@@ -477,6 +493,52 @@ __device__ __forceinline__ unsigned mword_shift_rep(const unsigned* M, const Geo
 // buffer that holds the result.  `src` must not be bufA or bufB's partner in use.
 constexpr int kErodeDirectMax = 10;     // radii up to this take one direct pass per axis
 
+// Vertical AND over the rows y-R .. y+R (clamped: the edge row replicated) for a segment of eight rows of one word
+// column: the 8 + 2R rows are read once and the windows are built by doubling in registers
+// (spans 1, 2, 4, .. then one overlapped pair), about 7 ANDs and 2.5 loads per output word at R = 6 instead of 12 + 12.
+template <int R>
+__device__ __forceinline__ void erode_rows_seg(const unsigned* cur, unsigned* nxt, const Geom& g) {
+    constexpr int S = 8, N = S + 2 * R, W = 2 * R + 1;
+    constexpr int PW = W >= 16 ? 16 : (W >= 8 ? 8 : (W >= 4 ? 4 : 2));      // largest power of two <= W (W >= 3)
+    const int nseg = (g.h + S - 1) / S;
+    const int ntask = nseg * g.wpr;
+    const int hm1 = g.h - 1;
+    for (int t = threadIdx.x; t < ntask; t += kThreads) {
+        int sg, c; word_rc(g, t, sg, c);
+        const int y0 = sg * S;
+        unsigned a[N];
+        if (y0 - R >= 0 && y0 + S - 1 + R <= hm1) {
+            const unsigned* p = cur + (y0 - R) * g.wpr + c;
+#pragma unroll
+            for (int k = 0; k < N; ++k) { a[k] = *p; p += g.wpr; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) a[k] = cur[min(max(y0 - R + k, 0), hm1) * g.wpr + c];
+        }
+        // a[i] = AND of rows i .. i + span - 1
+#pragma unroll
+        for (int i = 0; i + 2 <= N; ++i) a[i] &= a[i + 1];
+        if (PW >= 4) {
+#pragma unroll
+            for (int i = 0; i + 4 <= N; ++i) a[i] &= a[i + 2];
+        }
+        if (PW >= 8) {
+#pragma unroll
+            for (int i = 0; i + 8 <= N; ++i) a[i] &= a[i + 4];
+        }
+        if (PW >= 16) {
+#pragma unroll
+            for (int i = 0; i + 16 <= N; ++i) a[i] &= a[i + 8];
+        }
+        unsigned* o = nxt + y0 * g.wpr + c;
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            if (y0 + i <= hm1) *o = a[i] & a[i + W - PW];
+            o += g.wpr;
+        }
+    }
+}
+
 VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsigned* bufB, const Geom& g, int r) {
     const unsigned* cur = src;
     unsigned* nxt = (src == bufA) ? bufB : bufA;
@@ -498,12 +560,18 @@ VI_PHASE unsigned* erode_square_bits(const unsigned* src, unsigned* bufA, unsign
         cta_sync();
         cur = nxt;
         nxt = (cur == bufA) ? bufB : bufA;
-        // vertical: AND of the 2r+1 rows (edge row replicated)
-        for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
-            int y, c; word_rc(g, i, y, c);
-            unsigned v = cur[i];
-            for (int d = 1; d <= r; ++d) v &= cur[max(y - d, 0) * g.wpr + c] & cur[min(y + d, g.h - 1) * g.wpr + c];
-            nxt[i] = v;
+        // vertical: AND of the 2r+1 rows (edge row replicated), eight rows of one word column per thread
+        switch (r) {
+            case 1: erode_rows_seg<1>(cur, nxt, g); break;
+            case 2: erode_rows_seg<2>(cur, nxt, g); break;
+            case 3: erode_rows_seg<3>(cur, nxt, g); break;
+            case 4: erode_rows_seg<4>(cur, nxt, g); break;
+            case 5: erode_rows_seg<5>(cur, nxt, g); break;
+            case 6: erode_rows_seg<6>(cur, nxt, g); break;
+            case 7: erode_rows_seg<7>(cur, nxt, g); break;
+            case 8: erode_rows_seg<8>(cur, nxt, g); break;
+            case 9: erode_rows_seg<9>(cur, nxt, g); break;
+            default: erode_rows_seg<10>(cur, nxt, g); break;
         }
         cta_sync();
         return nxt;

@@ -96,9 +96,10 @@ VI_PHASE void prefetch_crop_l2(const KArgs& a, int uid) {
 }
 
 // Warp 0 only (the caller synchronises).
-__device__ inline void select_levels(UnitShared& sh, int npix, int thr, int t) {
-    // Six levels around the two Otsu class medians of the (blurred) histogram.
-    // Any level set is exact; these make the cell brackets decide nearly every pixel.
+__device__ inline void select_levels(UnitShared& sh, int npix, int thr, int t, bool bright) {
+    // Three levels around the median of one Otsu class of the (blurred) histogram: the dark class (the seg mask is an
+    // inverse threshold, so the ROI lives there), or the bright one when a caller-supplied mask does (detect_defects).
+    // Any level set is exact; these make the cell brackets decide nearly every pixel of the ROI.
     {
         const int lane = lane_id();
         unsigned c[8], tot = 0;
@@ -114,29 +115,22 @@ __device__ inline void select_levels(UnitShared& sh, int npix, int thr, int t) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { unsigned v = __shfl_sync(kFull, c[k], t >> 3); if (k == (t & 7)) ct = v; }
         const unsigned nd = at_t + ct, nb = (unsigned)npix - nd;
-        const unsigned tgt_d = (nd + 1) / 2, tgt_b = nd + (nb + 1) / 2;
+        const unsigned ncls = bright ? nb : nd;
+        const unsigned tgt = bright ? nd + (nb + 1) / 2 : (nd + 1) / 2;
         // first bin whose cumulative count reaches the target
-        unsigned fd = 0xffffu, fb = 0xffffu;
+        unsigned f = 0xffffu;
 #pragma unroll
         for (int k = 7; k >= 0; --k) {
             const unsigned cum = base + c[k];
-            if (nd && cum >= tgt_d) fd = lane * 8 + k;
-            if (nb && cum >= tgt_b) fb = lane * 8 + k;
+            if (ncls && cum >= tgt) f = lane * 8 + k;
         }
-        fd = __reduce_min_sync(kFull, fd);
-        fb = __reduce_min_sync(kFull, fb);
+        f = __reduce_min_sync(kFull, f);
         if (lane == 0) {
-            const int cd = nd ? (int)fd : t, cb = nb ? (int)fb : t;
+            const int cm = ncls ? (int)f : t;
             int s = 1;
             const int lim = thr / 3 > 1 ? thr / 3 : 1;
             while (s * 2 <= lim && s < 16) s *= 2;
-            int l0 = cd - s, l1 = cd, l2 = cd + s, l3 = cb - s, l4 = cb, l5 = cb + s;
-            // cd <= t < cb, so only l2 / l3 can be out of order: a 2-element swap sorts the list
-            if (l2 > l3) { int x = l2; l2 = l3; l3 = x; }
-            if (l1 > l2) { int x = l1; l1 = l2; l2 = x; }
-            if (l3 > l4) { int x = l3; l3 = l4; l4 = x; }
-            sh.levels[0] = min(254, max(0, l0)); sh.levels[1] = min(254, max(0, l1)); sh.levels[2] = min(254, max(0, l2));
-            sh.levels[3] = min(254, max(0, l3)); sh.levels[4] = min(254, max(0, l4)); sh.levels[5] = min(254, max(0, l5));
+            sh.levels[0] = min(254, max(0, cm - s)); sh.levels[1] = min(254, max(0, cm)); sh.levels[2] = min(254, max(0, cm + s));
         }
     }
     __syncwarp();
@@ -259,6 +253,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     const bool need_gray = mode == MODE_FULL || mode == MODE_SEG_ONLY || mode == MODE_DETECT;
     const bool need_seg = mode == MODE_FULL || mode == MODE_SEG_ONLY;
     int otsu_t = 0, dx = 0, dy = 0, n_runs_max = 0;
+    bool lattice = false;
     double cx = __longlong_as_double(0x7ff8000000000000ll), cy = cx;
     unsigned seg_area = 0;
 
@@ -293,7 +288,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             blur_general(gray, g, cfg_blur_k, a.taps, g_hp, g_blur);
         }
         unsigned* hist_base = reinterpret_cast<unsigned*>(GMEM ? hist_smem : Rg);
-        for (int i = tid; i < plan.n_hist * kHistWords; i += kThreads) hist_base[i] = 0;
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(hist_base);                  // 128-bit stores: the copies are 16-byte aligned
+            for (int i = tid; i < plan.n_hist * (kHistWords / 4); i += kThreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (tid < 256) sh.hist[tid] = 0;
         cta_sync();
         pt.acc(30);
@@ -316,19 +314,45 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             }
         }
         pt.tick();   // 1 blur + histogram
-        // ---- P2: Otsu.  The exact scan is a serial recurrence in doubles: one warp advances it in slices while
-        // the others walk the columns of the median stage's cell pass, which needs no mask and only approximate
-        // levels (an approximate threshold splits the histogram into its classes).
+        // ---- P2: Otsu.  The exact scan is a serial recurrence in doubles: one warp runs it while the others walk the
+        // columns of the median stage's cell pass, which needs no mask and only approximate levels (an approximate
+        // threshold splits the histogram into its classes).  The stage's workspace is the region of the masks after
+        // the first one: none of them is live before the threshold (the first holds a caller-supplied mask in
+        // MODE_DETECT).
         double* ows = reinterpret_cast<double*>(WS + plan.ws_bytes - kOtsuWsBytes);
-        const bool lattice = SPEC || ((mode == MODE_FULL || mode == MODE_DETECT) && cfg_defect_method == 0 && g.w <= kRankMaxW &&
-                                      rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes);
-        RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
+        lattice = SPEC || ((mode == MODE_FULL || mode == MODE_DETECT) && cfg_defect_method == 0 &&
+                           rank_ws_bytes(g.w, g.h) + kOtsuWsBytes <= (long long)(kNumMasks - 1) * plan.mask_bytes + plan.ws_bytes);
+        RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
+        const bool vote = !SPEC && mode == MODE_DETECT && lattice;
+        if (vote) { load_mask_bits(aux, g, MA); }       // the caller's mask decides which class the levels bracket
         if (warp_id() == 0) {                       // one warp, no barriers in between: approximate threshold, levels, tables
             int last;
             const int ta = otsu_approx_warp(sh.hist, npix, last);
             if (lane_id() == 0) { sh.t_apx = ta; sh.otsu_last = last; }
-            if (lattice) {
-                select_levels(sh, npix, a.p.threshold, ta);
+            if (lattice && !vote) {
+                select_levels(sh, npix, a.p.threshold, ta, false);
+                rank_tables(sh.levels, a.p.threshold, rw);
+            }
+        } else if (lattice) {
+            rank_cmm(gray, g, rw, 1);               // the cells' gray min / max need no level: 15 warps, meanwhile
+        }
+        if (vote) {
+            // one sample per mask word: is the mask's class the dark one or the bright one?
+            cta_sync();
+            const int ta = sh.t_apx;
+            unsigned long long v = 0;
+            for (int i = tid; i < g.nwords; i += kThreads) {
+                const unsigned m = MA[i];
+                if (m) {
+                    int y, c; word_rc(g, i, y, c);
+                    const int x = c * 32 + __ffs(m) - 1;
+                    v += 1ull + ((int)gray[y * g.gp + x] <= ta ? (1ull << 32) : 0ull);
+                }
+            }
+            v = cta_sum_u64(cta, v);
+            const bool bright = 2 * (v >> 32) < (v & 0xffffffffull);
+            if (warp_id() == 0) {
+                select_levels(sh, npix, a.p.threshold, ta, bright);
                 rank_tables(sh.levels, a.p.threshold, rw);
             }
         }
@@ -424,7 +448,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         }
     }
 
-    if (mode == MODE_FILL || mode == MODE_STATS || mode == MODE_ERODE || mode == MODE_LABEL || mode == MODE_DETECT) {
+    if (mode == MODE_FILL || mode == MODE_STATS || mode == MODE_ERODE || mode == MODE_LABEL || (mode == MODE_DETECT && !lattice)) {
         load_mask_bits(aux, g, MA);
         cta_sync();
     }
@@ -508,9 +532,9 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     // ---- P11: median residual (second part: the dirty cells against the ROI) ------------
     for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
     cta_sync();
-    if (SPEC || (g.w <= kRankMaxW && rank_ws_bytes(g.w) + kOtsuWsBytes <= plan.ws_bytes)) {
-        RankWs rw = rank_ws_carve(WS, g.w, g_rank, a.wmax, a.hmax, sh.rank_cnt);
-        n_amb = rank_finish(gray, g, rw, thr, MD, MC, pt);
+    if (SPEC || lattice) {
+        RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
+        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, MC, pt);
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
