@@ -10,7 +10,7 @@ import vi_b200
 from vi_b200 import synth, _lib
 from vi_b200.grid import Grid, generate_grid
 
-NAMES = ["gather", "blur+hist", "approx thr+tables", "cells rest+otsu wait", "threshold", "close/open", "hole fill",
+NAMES = ["gather", "blur+hist", "wait for cell min/max", "cells rest+otsu wait", "threshold", "close/open", "hole fill",
          "centroid ccl", "excl+seg out", "erosion", "roi ccl", "dirty+exact", "open3", "defect hole fill", "area filter",
          "defect out"]
 
@@ -39,7 +39,7 @@ def main():
     print(f"{n} images, {n*48} units, kernel {e0.elapsed_time(e1):.3f} ms; mean cycles/unit {mean.sum():.0f} (phase slots {tot:.0f} + sub-phase slots {mean[len(NAMES):].sum():.0f})")
     for i, nm in enumerate(NAMES):
         print(f"  {i:2d} {nm:18s} {mean[i]:10.0f}  {100*mean[i]/tot:5.1f}%   max {p[:, i].max():10.0f}")
-    for i, nm in ((20, "rank: V"), (21, "rank: S+C"), (22, "rank: classify"), (23, "ccl: count+scan"), (24, "ccl: extract"), (25, "ccl: link"), (26, "ccl: jump B"), (27, "ccl: unions"), (28, "ccl: jump D"), (29, "thr: gray mask"), (30, "hist: zero"), (31, "hist: blur3 loop"), (32, "gather: wait for rows")):
+    for i, nm in ((20, "rank: V"), (21, "rank: C"), (22, "rank: classify"), (23, "ccl: count+scan"), (24, "ccl: extract"), (25, "ccl: link"), (26, "ccl: jump B"), (27, "ccl: unions"), (28, "ccl: jump D"), (29, "thr: gray mask"), (30, "hist: zero"), (31, "hist: blur3 loop"), (32, "gather: wait for rows"), (33, "warp0: approx thr"), (34, "warp0: levels+tables")):
         print(f"  {i:2d} {nm:18s} {mean[i]:10.0f}")
     print("  gather cycles: first unit of each CTA %.0f, later units %.0f" % (p[:148, 0].mean(), p[148:, 0].mean()))
     print("  n_ambiguous mean %.1f max %d; n_runs max %d" % (rec['n_ambiguous'].mean(), rec['n_ambiguous'].max(), rec['n_runs'].max()))

@@ -298,6 +298,8 @@ struct PhaseTimerT {
 
 __device__ __forceinline__ void cta_sync() { __syncthreads(); }
 __device__ __forceinline__ int cta_sync_or(int pred) { return __syncthreads_or(pred); }
+// Barrier of the first `nthreads` threads only (named barrier 1): phases that one warp sits out.
+__device__ __forceinline__ void workers_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

@@ -57,7 +57,7 @@ struct RankWs {
     unsigned* plane;     // [ntasks] per C task: 6 codes (4 bits each) | 6 dirty bits << 24, in the CTA's global scratch
     unsigned* exact;     // [exact_cap] ambiguous pixels (y << 16 | x), global scratch; more are counted inline
     int exact_cap;
-    int* counters;       // shared: [1] ambiguous pixels listed, [2] ambiguous pixels total
+    int* counters;       // shared: [0] dirty cells in the ROI, [1] ambiguous pixels listed, [2] ambiguous pixels total
     int P, cpitch, nlx, nly, ngrp, nrb;
     int plane_cap;       // words the plane holds (CHECKED builds)
 };
@@ -173,10 +173,10 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
 
 // M: gray min / max of every cell (pixels past the crop edge repeat the edge pixel: duplicates change neither).
 // Runs on the warps first_warp .. kWarps-1.
-VI_PHASE void rank_cmm(const uint8_t* gray, const Geom& g, const RankWs& w, int first_warp) {
-    const int nth = (kWarps - first_warp) * 32;
+VI_PHASE void rank_cmm(const uint8_t* gray, const Geom& g, const RankWs& w, int first_warp, int end_warp) {
+    const int nth = (end_warp - first_warp) * 32;
     const int t0 = (int)threadIdx.x - first_warp * 32;
-    if (t0 < 0) return;
+    if (t0 < 0 || t0 >= nth) return;
     const int hm1 = g.h - 1, wm1 = g.w - 1, gp = g.gp;
     const int ncell = w.nlx * w.nly;
     const unsigned mx = magic_of((unsigned)w.nlx);
@@ -266,127 +266,150 @@ __device__ __forceinline__ unsigned rank_group_cells(const RankWs& w, int j, int
     return word;
 }
 
+// Cells per warp of the V pass: full warps for wide units (the pass is issue bound there); narrow units spread their
+// few columns over all warps instead (latency bound otherwise).
+__device__ __forceinline__ int rank_cpw(int nslot) { return nslot > 64 ? kColsPerWarp / kCell : max((nslot + kWarps - 1) / kWarps, 1); }
+// The warp kOtsuWarp owns no column of the V pass: it can run the exact Otsu scan beside the whole stage.
+__device__ __forceinline__ bool rank_otsu_aside(const Geom& g) {
+    const int nslot = rank_nlx(g.w) + 2 * kVPad;
+    return kOtsuWarp * rank_cpw(nslot) >= nslot;
+}
+
 // Part 1 (needs only the gray crop and the levels; the caller has run rank_cmm): window counts on the lattice, the
-// plane of dirty cells.  The warp kOtsuWarp runs the exact Otsu scan meanwhile when it owns no column (else after
-// its columns); *otsu_t holds the threshold on return.
+// plane of dirty cells.  `oside`: the warp kOtsuWarp is busy with the exact Otsu scan (started by the caller) and
+// joins at the final barrier only; else it runs the scan here after its columns.  *otsu_t holds the threshold on return.
 template <class PT>
 VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, const unsigned* hist, int npix,
-                         double* ows, int olast, int* otsu_t, PT& pt) {
+                         double* ows, int olast, int* otsu_t, bool oside, PT& pt) {
     const int lane = lane_id(), warp = warp_id();
     const int nly = w.nly, nlx = w.nlx;
     const int hm1 = g.h - 1, wm1 = g.w - 1;
     const int nslot = nlx + 2 * kVPad;                           // cell slots of a row: 3 virtual, the cells, 3 virtual
-    // cells per warp: full warps for wide units (the pass is issue bound there); narrow units spread their few
-    // columns over all warps instead (latency bound otherwise)
-    const int cpw = nslot > 64 ? kColsPerWarp / kCell : max((nslot + kWarps - 1) / kWarps, 1);
+    const int cpw = rank_cpw(nslot);
     const int nround = (nslot + kWarps * cpw - 1) / (kWarps * cpw);
-    const unsigned T = (unsigned)(lv[0] + 512) | ((unsigned)(lv[1] + 512) << 10) | ((unsigned)(lv[2] + 512) << 20);
-    int P = w.P, gp = g.gp;
-    asm volatile("" : "+r"(P), "+r"(gp));                        // opaque strides (else re-derived from the unit width per store)
     const bool owarp = warp == kOtsuWarp;
-    const bool ocols = kOtsuWarp * cpw < nslot;                  // the Otsu warp owns columns: its scan comes after them
-    if (owarp && !ocols) {
-        OtsuJob job;
-        otsu_begin(job, hist, npix, ows, olast);
-        const int t = otsu_end(job);
-        if (lane == 0) *otsu_t = t;
-    }
-    const int nit = (nly + 7) >> 3;
-    for (int rd = 0; rd < nround; ++rd) {
-        const int slot0 = (rd * kWarps + warp) * cpw;            // first cell slot of this warp
-        if (slot0 >= nslot) continue;
-        const int vcol = kCell * (slot0 - kVPad) + lane;         // may lie left / right of the crop: replicated border
-        const uint8_t* gcol = gray + min(max(vcol, 0), wm1);
-        const int slot = slot0 + lane / kCell;
-        const bool lead = lane < cpw * kCell && (lane % kCell) == 0 && slot < nslot;
-        unsigned* csp = w.cs + (lead ? slot : P - 1);
-        VI_CHECK(!lead || slot < P - 1, CHK_LATTICE_SLOT);
-        VState st;
-        {
-            // prologue: blocks b = -3 .. 2 (rows above the crop replicate row 0)
-            const unsigned g0 = gcol[0];
-            const unsigned Ba = ind3(T, g0, g0, g0);
-            st.S = 3 * Ba;
-            st.r[0] = st.r[1] = st.r[2] = Ba;
-            st.r[6] = st.r[7] = 0;
+    if (!(oside && owarp)) {
+        const unsigned T = (unsigned)(lv[0] + 512) | ((unsigned)(lv[1] + 512) << 10) | ((unsigned)(lv[2] + 512) << 20);
+        int P = w.P, gp = g.gp;
+        asm volatile("" : "+r"(P), "+r"(gp));                    // opaque strides (else re-derived from the unit width per store)
+        const int nit = (nly + 7) >> 3;
+        for (int rd = 0; rd < nround; ++rd) {
+            const int slot0 = (rd * kWarps + warp) * cpw;        // first cell slot of this warp
+            if (slot0 >= nslot) continue;
+            const int vcol = kCell * (slot0 - kVPad) + lane;     // may lie left / right of the crop: replicated border
+            const uint8_t* gcol = gray + min(max(vcol, 0), wm1);
+            const int slot = slot0 + lane / kCell;
+            const bool lead = lane < cpw * kCell && (lane % kCell) == 0 && slot < nslot;
+            unsigned* csp = w.cs + (lead ? slot : P - 1);
+            VI_CHECK(!lead || slot < P - 1, CHK_LATTICE_SLOT);
+            VState st;
+            {
+                // prologue: blocks b = -3 .. 2 (rows above the crop replicate row 0)
+                const unsigned g0 = gcol[0];
+                const unsigned Ba = ind3(T, g0, g0, g0);
+                st.S = 3 * Ba;
+                st.r[0] = st.r[1] = st.r[2] = Ba;
+                st.r[6] = st.r[7] = 0;
 #pragma unroll
-            for (int bb = 0; bb < 3; ++bb) {
-                const unsigned B = ind3(T, gcol[min(3 * bb, hm1) * gp], gcol[min(3 * bb + 1, hm1) * gp], gcol[min(3 * bb + 2, hm1) * gp]);
-                st.S += B;
-                st.r[3 + bb] = B;
+                for (int bb = 0; bb < 3; ++bb) {
+                    const unsigned B = ind3(T, gcol[min(3 * bb, hm1) * gp], gcol[min(3 * bb + 1, hm1) * gp], gcol[min(3 * bb + 2, hm1) * gp]);
+                    st.S += B;
+                    st.r[3 + bb] = B;
+                }
+                st.q0 = gcol[min(9, hm1) * gp]; st.q1 = gcol[min(10, hm1) * gp]; st.q2 = gcol[min(11, hm1) * gp];
             }
-            st.q0 = gcol[min(9, hm1) * gp]; st.q1 = gcol[min(10, hm1) * gp]; st.q2 = gcol[min(11, hm1) * gp];
+            for (int it = 0; it < nit; ++it) {
+                const int j0 = 8 * it;
+                if (kCell * (j0 + 8 + 3) + 2 <= hm1) v_oct<false>(st, T, gcol, gp, hm1, j0, csp, P);
+                else v_oct<true>(st, T, gcol, gp, hm1, j0, csp, P);
+                csp += 8 * P;
+            }
         }
-        for (int it = 0; it < nit; ++it) {
-            const int j0 = 8 * it;
-            if (kCell * (j0 + 8 + 3) + 2 <= hm1) v_oct<false>(st, T, gcol, gp, hm1, j0, csp, P);
-            else v_oct<true>(st, T, gcol, gp, hm1, j0, csp, P);
-            csp += 8 * P;
+        if (owarp) {                                             // (not aside: the scan follows this warp's columns)
+            OtsuJob job;
+            otsu_begin(job, hist, npix, ows, olast);
+            const int t = otsu_end(job);
+            if (lane == 0) *otsu_t = t;
         }
-    }
-    if (owarp && ocols) {
-        OtsuJob job;
-        otsu_begin(job, hist, npix, ows, olast);
-        const int t = otsu_end(job);
-        if (lane == 0) *otsu_t = t;
+        if (oside) workers_sync(kThreads - 32); else cta_sync();
+        pt.acc(20);
+        // ---- C: one thread per (lattice row, group of kGrp cells); half-warps over 16 consecutive rows ------------
+        {
+            const int nhw = w.nrb * w.ngrp;
+            const unsigned mr = magic_of((unsigned)w.nrb);
+            const int nhalf = (oside ? kThreads - 32 : kThreads) / 16;
+            for (int hb = (int)(threadIdx.x >> 4); hb < nhw; hb += nhalf) {
+                const int gi = (int)magic_div((unsigned)hb, (unsigned)w.nrb, mr), rb = hb - gi * w.nrb;
+                const int j = rb * 16 + (int)(threadIdx.x & 15);
+                unsigned word = 0;
+                if (j < nly) word = rank_group_cells(w, j, gi);
+                VI_CHECK(hb * 16 + 15 < w.plane_cap, CHK_DIRTY_LIST);
+                w.plane[hb * 16 + (threadIdx.x & 15)] = word;
+            }
+        }
+        pt.acc(21);
     }
     cta_sync();
-    pt.acc(20);
-    // ---- C: one thread per (lattice row, group of kGrp cells); half-warps over 16 consecutive rows ----------------
-    {
-        const int nhw = w.nrb * w.ngrp;
-        const unsigned mr = magic_of((unsigned)w.nrb);
-        for (int hb = (int)(threadIdx.x >> 4); hb < nhw; hb += kThreads / 16) {
-            const int gi = (int)magic_div((unsigned)hb, (unsigned)w.nrb, mr), rb = hb - gi * w.nrb;
-            const int j = rb * 16 + (int)(threadIdx.x & 15);
-            unsigned word = 0;
-            if (j < nly) word = rank_group_cells(w, j, gi);
-            VI_CHECK(hb * 16 + 15 < w.plane_cap, CHK_DIRTY_LIST);
-            w.plane[hb * 16 + (threadIdx.x & 15)] = word;
-        }
-    }
-    cta_sync();
-    pt.acc(21);
 }
 
 // Part 2 (needs the ROI): CAND (zeroed by the caller) receives every ROI pixel with |g - med| > thr.
 // Returns the number of pixels that needed an exact rank count.
 template <class PT>
 VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, int thr, const unsigned* ROI, unsigned* CAND,
-                         PT& pt) {
+                         unsigned* clist, int ccap, PT& pt) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const int hm1 = g.h - 1, wm1 = g.w - 1;
-    // ---- dirty cells that touch the ROI: per-pixel classification ----------------------
+    // ---- dirty cells that touch the ROI: listed (they cluster along the plate edge: whole tasks of them), then
+    // classified per pixel one cell per thread.  `clist` / `ccap`: a list in shared memory; what does not fit is
+    // classified on the spot.
     {
         const int ntask = w.nrb * w.ngrp * 16;
         const unsigned mr = magic_of((unsigned)w.nrb);
-        for (int t = tid; t < ntask; t += kThreads) {
-            const unsigned word = w.plane[t];
-            unsigned d = word >> 24;
-            if (!d) continue;
-            const int hb = t >> 4;
-            const int gi = (int)magic_div((unsigned)hb, (unsigned)w.nrb, mr), rb = hb - gi * w.nrb;
-            const int j = rb * 16 + (t & 15);
-            // ROI bits of the 18-pixel strip of the task's cells, three rows OR-ed, then one bit per cell
-            const int x0 = kCell * kGrp * gi, c0 = x0 >> 5, sh = x0 & 31;
-            unsigned b = 0;
+        for (int t0 = 0; t0 < ntask; t0 += 4 * kThreads) {
+            unsigned wd[4];
 #pragma unroll
-            for (int rr = 0; rr < kCell; ++rr) {
-                const int y = kCell * j + rr;
-                if (y <= hm1) {
-                    const unsigned* row = ROI + y * g.wpr;
-                    const unsigned lo = row[c0], hi = c0 + 1 < g.wpr ? row[c0 + 1] : 0u;
-                    b |= __funnelshift_r(lo, hi, sh);
+            for (int q = 0; q < 4; ++q) { const int t = t0 + q * kThreads + tid; wd[q] = t < ntask ? w.plane[t] : 0u; }      // four loads in flight
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned word = wd[q];
+                unsigned d = word >> 24;
+                if (!d) continue;
+                const int t = t0 + q * kThreads + tid;
+                const int hb = t >> 4;
+                const int gi = (int)magic_div((unsigned)hb, (unsigned)w.nrb, mr), rb = hb - gi * w.nrb;
+                const int j = rb * 16 + (t & 15);
+                // ROI bits of the 18-pixel strip of the task's cells, three rows OR-ed, then one bit per cell
+                const int x0 = kCell * kGrp * gi, c0 = x0 >> 5, sh = x0 & 31;
+                unsigned b = 0;
+#pragma unroll
+                for (int rr = 0; rr < kCell; ++rr) {
+                    const int y = kCell * j + rr;
+                    if (y <= hm1) {
+                        const unsigned* row = ROI + y * g.wpr;
+                        const unsigned lo = row[c0], hi = c0 + 1 < g.wpr ? row[c0 + 1] : 0u;
+                        b |= __funnelshift_r(lo, hi, sh);
+                    }
+                }
+                b |= (b >> 1) | (b >> 2);                                   // bit 3k: any pixel of cell k
+                const unsigned cells = (b & 1u) | ((b >> 2) & 2u) | ((b >> 4) & 4u) | ((b >> 6) & 8u) | ((b >> 8) & 16u) | ((b >> 10) & 32u);
+                d &= cells;
+                if (!d) continue;
+                const int nc = __popc(d);
+                int k = atomicAdd(&w.counters[0], nc);
+                while (d) {
+                    const int m = __ffs(d) - 1; d &= d - 1;
+                    const unsigned code = (word >> (4 * m)) & 15u;
+                    if (k < ccap) clist[k] = ((unsigned)j << 16) | ((unsigned)(kGrp * gi + m) << 4) | code;
+                    else rank_dirty_cell(gray, g, thr, ROI, CAND, w, kGrp * gi + m, j, rank_code_thresholds(lv, thr, (int)code));
+                    ++k;
                 }
             }
-            b |= (b >> 1) | (b >> 2);                                   // bit 3k: any pixel of cell k
-            const unsigned cells = (b & 1u) | ((b >> 2) & 2u) | ((b >> 4) & 4u) | ((b >> 6) & 8u) | ((b >> 8) & 16u) | ((b >> 10) & 32u);
-            d &= cells;
-            while (d) {
-                const int m = __ffs(d) - 1; d &= d - 1;
-                const unsigned cw = rank_code_thresholds(lv, thr, (int)((word >> (4 * m)) & 15u));
-                rank_dirty_cell(gray, g, thr, ROI, CAND, w, kGrp * gi + m, j, cw);
-            }
+        }
+        cta_sync();
+        const int nlist = min(w.counters[0], ccap);
+        for (int k = tid; k < nlist; k += kThreads) {
+            const unsigned e = clist[k];
+            rank_dirty_cell(gray, g, thr, ROI, CAND, w, (int)((e >> 4) & 0xfffu), (int)(e >> 16), rank_code_thresholds(lv, thr, (int)(e & 15u)));
         }
     }
     cta_sync();

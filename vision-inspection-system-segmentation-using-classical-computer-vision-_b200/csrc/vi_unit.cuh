@@ -325,16 +325,27 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
         const bool vote = !SPEC && mode == MODE_DETECT && lattice;
         if (vote) { load_mask_bits(aux, g, MA); }       // the caller's mask decides which class the levels bracket
+        // the exact Otsu scan starts now on its own warp when that warp owns no column of the cell pass
+        const bool oside = lattice && !vote && rank_otsu_aside(g);
         if (warp_id() == 0) {                       // one warp, no barriers in between: approximate threshold, levels, tables
             int last;
             const int ta = otsu_approx_warp(sh.hist, npix, last);
             if (lane_id() == 0) { sh.t_apx = ta; sh.otsu_last = last; }
+            pt.acc(33);
             if (lattice && !vote) {
                 select_levels(sh, npix, a.p.threshold, ta, false);
                 rank_tables(sh.levels, a.p.threshold, rw);
             }
+            pt.acc(34);
+        } else if (oside && warp_id() == kOtsuWarp) {
+            int last;
+            otsu_approx_warp(sh.hist, npix, last);  // (the same bound warp 0 derives: no hand-over to wait for)
+            OtsuJob job;
+            otsu_begin(job, sh.hist, npix, ows, last);
+            const int t = otsu_end(job);
+            if (lane_id() == 0) sh.otsu_t = t;
         } else if (lattice) {
-            rank_cmm(gray, g, rw, 1);               // the cells' gray min / max need no level: 15 warps, meanwhile
+            rank_cmm(gray, g, rw, 1, oside ? kWarps - 1 : kWarps);     // the cells' gray min / max need no level: meanwhile
         }
         if (vote) {
             // one sample per mask word: is the mask's class the dark one or the bright one?
@@ -356,10 +367,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
                 rank_tables(sh.levels, a.p.threshold, rw);
             }
         }
-        cta_sync();
+        if (oside) { if (warp_id() != kOtsuWarp) workers_sync(kThreads - 32); } else cta_sync();
         if (lattice) {
             pt.tick();   // 2 approximate threshold, levels, tables
-            rank_cells(gray, g, rw, sh.levels, sh.hist, npix, ows, sh.otsu_last, &sh.otsu_t, pt);
+            rank_cells(gray, g, rw, sh.levels, sh.hist, npix, ows, sh.otsu_last, &sh.otsu_t, oside, pt);
         } else {
             if (warp_id() == kOtsuWarp) {
                 OtsuJob job;
@@ -534,7 +545,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     cta_sync();
     if (SPEC || lattice) {
         RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
-        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, MC, pt);
+        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, MC, reinterpret_cast<unsigned*>(WS), min(plan.ws_bytes >> 2, 4096), pt);
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
