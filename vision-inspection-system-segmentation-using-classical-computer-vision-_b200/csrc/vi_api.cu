@@ -285,7 +285,7 @@ extern "C" int vi_set_ref_centroids(vi_ctx* c, const double* cxcy, int n_units, 
     return VI_OK;
 }
 
-// Diagnostics: div_by_rcp against the IEEE divide on pseudo-random operand pairs drawn like
+// Diagnostics: div_y / div_with_y against the IEEE divide on pseudo-random operand pairs drawn like
 // the Otsu recurrence's (numerator in [0, 256), divisor in (2^-24, 1]), plus divisors with
 // long runs of one bits in the significand.
 __global__ void fastdiv_check_kernel(unsigned long long seed, long long per_thread, unsigned long long* bad) {
@@ -304,8 +304,7 @@ __global__ void fastdiv_check_kernel(unsigned long long seed, long long per_thre
         const int en = 1023 + 7 - (int)((s >> 60) % 12);            // numerator in [2^-4, 256)
         const double b = __longlong_as_double(((long long)eb << 52) | (long long)m2);
         const double n = __longlong_as_double(((long long)en << 52) | (long long)m1);
-        const double r = __ddiv_rn(1.0, b);
-        const double q = vi::div_by_rcp(n, b, r), ref = __ddiv_rn(n, b);
+        const double q = vi::div_with_y(n, b, vi::div_y(b)), ref = __ddiv_rn(n, b);
         if (__double_as_longlong(q) != __double_as_longlong(ref)) ++nbad;
     }
     if (nbad) atomicAdd(bad, nbad);

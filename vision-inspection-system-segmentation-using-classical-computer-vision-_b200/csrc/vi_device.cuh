@@ -105,10 +105,13 @@ __host__ __device__ inline int rank_ngrp(int w) { return (rank_nlx(w) + kGrp - 1
 // rows that the lanes of a half-warp hold land on distinct banks.
 __host__ __device__ inline int rank_P(int w) { return ((rank_nlx(w) + 2 * kVPad > kGrp * rank_ngrp(w) + 6 ? rank_nlx(w) + 2 * kVPad : kGrp * rank_ngrp(w) + 6) + 1) | 1; }
 // cmm pitch: every cell a C task can read, half of it odd (same bank argument for 16-bit entries).
-__host__ __device__ inline int rank_cpitch(int w) { return 2 * ((kGrp * rank_ngrp(w) + 1) / 2 | 1); }
+__host__ __device__ inline int rank_cpitch(int w) {
+    const int a = kGrp * rank_ngrp(w), b = 4 * ((rank_nlx(w) + 3) / 4);          // cells a C task reads / quads the min-max pass writes
+    return 2 * (((a > b ? a : b) + 1) / 2 | 1);
+}
 __host__ __device__ inline long long rank_ws_bytes(int w, int h) {
     const long long nly = (h + kCell - 1) / kCell;
-    return (((nly + 7) & ~7ll) * rank_P(w) * 4 + nly * rank_cpitch(w) * 2 + 64 + 15) & ~15ll;
+    return ((((nly + 7) & ~7ll) + 1) * rank_P(w) * 4 + nly * rank_cpitch(w) * 2 + 64 + 15) & ~15ll;      // (+1: the row before row 0)
 }
 
 
@@ -267,7 +270,7 @@ struct Cta {
 
 // Diagnostics: per-phase SM cycle counts of one unit (thread 0, after the barrier
 // that ends the phase), written only when KArgs::prof is set.
-constexpr int kProfSlots = 40;
+constexpr int kProfSlots = 48;
 struct PtState { long long* out; long long t; int k; int pad; };      // lives in shared memory: no registers held across phases
 // ON = false compiles every hook away (the production kernel); ON = true is the diagnostics kernel that
 // vi_debug_set_profile selects.
@@ -288,6 +291,15 @@ struct PhaseTimerT {
             s->k = k + 1; s->t = n;
         }
     }
+    // stamps for a warp other than thread 0's (lane 0 of it records): c = stamp(); ...; c = lap(slot, c);
+    __device__ __forceinline__ long long stamp() { return ON ? clock64() : 0ll; }
+    __device__ __forceinline__ long long lap(int slot, long long c0) {
+        if (!ON) return 0ll;
+        const long long n = clock64();
+        if ((threadIdx.x & 31) == 0 && s->out) s->out[slot] += n - c0;
+        return n;
+    }
+    __device__ __forceinline__ void count(int slot, int v) { if (ON && (threadIdx.x & 31) == 0 && s->out) s->out[slot] += v; }
     // sub-phase accounting: add the time since the last tick/acc to `slot` without consuming a phase slot
     __device__ __forceinline__ void acc(int slot) {
         if (!ON) return;

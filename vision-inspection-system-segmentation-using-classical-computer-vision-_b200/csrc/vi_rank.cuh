@@ -79,7 +79,7 @@ __device__ inline RankWs rank_ws_carve(unsigned char* base, const Geom& g, unsig
     r.nlx = rank_nlx(g.w); r.nly = (g.h + kCell - 1) / kCell;
     r.ngrp = rank_ngrp(g.w); r.nrb = (r.nly + 15) >> 4;
     r.P = rank_P(g.w); r.cpitch = rank_cpitch(g.w);
-    r.cs = reinterpret_cast<unsigned*>(base); base += ((r.nly + 7) & ~7) * r.P * 4;
+    r.cs = reinterpret_cast<unsigned*>(base) + r.P; base += (((r.nly + 7) & ~7) + 1) * r.P * 4;      // row -1 takes the V pass's first (empty) deferred store
     r.cmm = reinterpret_cast<unsigned short*>(base); base += r.nly * r.cpitch * 2;
     r.table = reinterpret_cast<unsigned*>(base);
     r.counters = counters;
@@ -112,14 +112,18 @@ __device__ inline void rank_tables(const int* lv, int thr, RankWs w) {
 }
 
 // Exact decision for one pixel: #(window <= g+thr) <= 220 or #(window <= g-thr-1) >= 221.
-__device__ inline bool rank_exact_pixel_thread(const uint8_t* gray, const Geom& g, int thr, int x, int y) {
-    const int gv = gray[y * g.gp + x];
+// (cold: the overflow path of the ambiguous-pixel list and units the lattice does not cover.  Kept out of line and
+// rolled: inlined into the nine pixels of a dirty cell it was a quarter of the kernel's instructions)
+__device__ __noinline__ bool rank_exact_pixel_thread(const uint8_t* gray, int gp, int w, int h, int thr, int x, int y) {
+    const int gv = gray[y * gp + x];
     const int pa = gv + thr, pb = gv - thr - 1;
     int ca = 0, cb = 0;
+#pragma unroll 1
     for (int dy = -10; dy <= 10; ++dy) {
-        const uint8_t* row = gray + min(max(y + dy, 0), g.h - 1) * g.gp;
+        const uint8_t* row = gray + min(max(y + dy, 0), h - 1) * gp;
+#pragma unroll 3
         for (int dx = -10; dx <= 10; ++dx) {
-            const int v = row[min(max(x + dx, 0), g.w - 1)];
+            const int v = row[min(max(x + dx, 0), w - 1)];
             ca += v <= pa;
             cb += v <= pb;
         }
@@ -165,31 +169,49 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
                 const int k = atomicAdd(&w.counters[1], 1);
                 VI_CHECK(k >= 0 && y < g.h && x < g.w, CHK_EXACT_LIST);
                 if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | (unsigned)x;
-                else if (rank_exact_pixel_thread(gray, g, thr, x, y)) atomicOr(&CAND[wi], bit);
+                else if (rank_exact_pixel_thread(gray, g.gp, g.w, g.h, thr, x, y)) atomicOr(&CAND[wi], bit);
             }
         }
     }
 }
 
-// M: gray min / max of every cell (pixels past the crop edge repeat the edge pixel: duplicates change neither).
-// Runs on the warps first_warp .. kWarps-1.
+// M: gray min / max of every cell, four cells (12 pixels = three gray words) per thread and step: the three rows are
+// reduced field-parallel on (even bytes, odd bytes) halves, then each cell's three columns.  Rows past the crop repeat
+// the last row; words past the crop's last word repeat it (their bytes past the crop edge hold in-crop pixels or stale
+// ones: a superset can only turn a clean cell dirty, never the reverse, and dirty cells are classified per pixel).
+// Runs on the warps first_warp .. end_warp-1.
 VI_PHASE void rank_cmm(const uint8_t* gray, const Geom& g, const RankWs& w, int first_warp, int end_warp) {
     const int nth = (end_warp - first_warp) * 32;
     const int t0 = (int)threadIdx.x - first_warp * 32;
     if (t0 < 0 || t0 >= nth) return;
-    const int hm1 = g.h - 1, wm1 = g.w - 1, gp = g.gp;
-    const int ncell = w.nlx * w.nly;
-    const unsigned mx = magic_of((unsigned)w.nlx);
-    for (int e = t0; e < ncell; e += nth) {
-        const int j = (int)magic_div((unsigned)e, (unsigned)w.nlx, mx), i = e - j * w.nlx;
-        const int x0 = kCell * i, x1 = min(x0 + 1, wm1), x2 = min(x0 + 2, wm1);
-        const uint8_t* r0 = gray + (kCell * j) * gp;
-        const uint8_t* r1 = gray + min(kCell * j + 1, hm1) * gp;
-        const uint8_t* r2 = gray + min(kCell * j + 2, hm1) * gp;
-        const unsigned a0 = r0[x0], a1 = r0[x1], a2 = r0[x2], b0 = r1[x0], b1 = r1[x1], b2 = r1[x2], c0 = r2[x0], c1 = r2[x1], c2 = r2[x2];
-        const unsigned mn = __vimin3_u32(__vimin3_u32(a0, a1, a2), __vimin3_u32(b0, b1, b2), __vimin3_u32(c0, c1, c2));
-        const unsigned mxv = __vimax3_u32(__vimax3_u32(a0, a1, a2), __vimax3_u32(b0, b1, b2), __vimax3_u32(c0, c1, c2));
-        w.cmm[j * w.cpitch + i] = (unsigned short)(mn | (mxv << 8));
+    const int hm1 = g.h - 1, wq = g.gp >> 2, nqm1 = ((g.w + 3) >> 2) - 1;
+    const int nquad = (w.nlx + 3) >> 2;
+    const int ntask = nquad * w.nly;
+    const unsigned mq = magic_of((unsigned)nquad);
+    const unsigned* gw = reinterpret_cast<const unsigned*>(gray);
+    for (int e = t0; e < ntask; e += nth) {
+        const int j = (int)magic_div((unsigned)e, (unsigned)nquad, mq), q = e - j * nquad;
+        const int k0 = min(3 * q, nqm1), k1 = min(3 * q + 1, nqm1), k2 = min(3 * q + 2, nqm1);
+        const unsigned* r0 = gw + (kCell * j) * wq;
+        const unsigned* r1 = gw + min(kCell * j + 1, hm1) * wq;
+        const unsigned* r2 = gw + min(kCell * j + 2, hm1) * wq;
+        const unsigned a0 = r0[k0], a1 = r0[k1], a2 = r0[k2], b0 = r1[k0], b1 = r1[k1], b2 = r1[k2], c0 = r2[k0], c1 = r2[k1], c2 = r2[k2];
+        constexpr unsigned F = 0x00FF00FFu;
+        // per word k: (bytes 0, 2) and (bytes 1, 3) of the column-wise min / max over the three rows
+        const unsigned en0 = __vimin3_u16x2(a0 & F, b0 & F, c0 & F), on0 = __vimin3_u16x2((a0 >> 8) & F, (b0 >> 8) & F, (c0 >> 8) & F);
+        const unsigned en1 = __vimin3_u16x2(a1 & F, b1 & F, c1 & F), on1 = __vimin3_u16x2((a1 >> 8) & F, (b1 >> 8) & F, (c1 >> 8) & F);
+        const unsigned en2 = __vimin3_u16x2(a2 & F, b2 & F, c2 & F), on2 = __vimin3_u16x2((a2 >> 8) & F, (b2 >> 8) & F, (c2 >> 8) & F);
+        const unsigned ex0 = __vimax3_u16x2(a0 & F, b0 & F, c0 & F), ox0 = __vimax3_u16x2((a0 >> 8) & F, (b0 >> 8) & F, (c0 >> 8) & F);
+        const unsigned ex1 = __vimax3_u16x2(a1 & F, b1 & F, c1 & F), ox1 = __vimax3_u16x2((a1 >> 8) & F, (b1 >> 8) & F, (c1 >> 8) & F);
+        const unsigned ex2 = __vimax3_u16x2(a2 & F, b2 & F, c2 & F), ox2 = __vimax3_u16x2((a2 >> 8) & F, (b2 >> 8) & F, (c2 >> 8) & F);
+        // cells: bytes (0,1,2) (3,4,5) (6,7,8) (9,10,11) of the 12; byte 4k -> e*k low, 4k+1 -> o*k low, 4k+2 -> e*k high, 4k+3 -> o*k high
+        const unsigned mn0 = __vimin3_u16x2(en0, on0, en0 >> 16) & 0xFFu, mx0 = __vimax3_u16x2(ex0, ox0, ex0 >> 16) & 0xFFu;
+        const unsigned mn1 = __vimin3_u16x2(on0 >> 16, en1, on1) & 0xFFu, mx1 = __vimax3_u16x2(ox0 >> 16, ex1, ox1) & 0xFFu;
+        const unsigned mn2 = __vimin3_u16x2(en1 >> 16, on1 >> 16, en2) & 0xFFu, mx2 = __vimax3_u16x2(ex1 >> 16, ox1 >> 16, ex2) & 0xFFu;
+        const unsigned mn3 = __vimin3_u16x2(on2, en2 >> 16, on2 >> 16) & 0xFFu, mx3 = __vimax3_u16x2(ox2, ex2 >> 16, ox2 >> 16) & 0xFFu;
+        unsigned* o = reinterpret_cast<unsigned*>(w.cmm + j * w.cpitch + 4 * q);           // cpitch is even: word aligned
+        o[0] = mn0 | (mx0 << 8) | (mn1 << 16) | (mx1 << 24);
+        o[1] = mn2 | (mx2 << 8) | (mn3 << 16) | (mx3 << 24);
     }
 }
 
@@ -205,35 +227,43 @@ __device__ __forceinline__ unsigned ind3(unsigned T, unsigned q0, unsigned q1, u
     return (lo + 2 * hi) >> 9;
 }
 
-// Column state of the V pass: the sliding 7-block sum and the ring of the last 8 block sums
-// (registers: the loop is unrolled by 8 so every ring index is static).
+// Column state of the V pass: the sliding 7-block sum, the ring of the last 8 block sums (registers: the loop is
+// unrolled by 8 so every ring index is static), the gray of the next two blocks (loaded two blocks ahead) and the
+// previous block's sum with its two shuffles in flight (stored one block later): a warp issues in order, so every
+// value it waits for was asked for a whole block earlier.
 struct VState {
     unsigned S;
     unsigned r[8];
-    unsigned q0, q1, q2;       // gray of the next block, loaded one block ahead
+    unsigned qa0, qa1, qa2, qb0, qb1, qb2;
+    unsigned pS, p1, p2;
 };
 
-// Eight lattice rows j0 .. j0+7 <-> blocks b = j0+3 .. j0+10 (sequence n = b+3, ring slot n & 7).
+// Eight lattice rows j0 .. j0+7 <-> blocks b = j0+3 .. j0+10 (sequence n = b+3, ring slot n & 7).  `csp` points at
+// row j0-1 of the thread's slot: the deferred store of the block before.
 template <bool CLAMP>
 __device__ __forceinline__ void v_oct(VState& st, unsigned T, const uint8_t* gcol, int gp, int hm1, int j0, unsigned* csp, int P) {
-    const uint8_t* pr = gcol + (kCell * (j0 + 4)) * gp;            // rows of block j0+4 (the first prefetch)
-    int rn = kCell * (j0 + 4);
+    const uint8_t* pr = gcol + (kCell * (j0 + 5)) * gp;            // rows of block j0+5 (the first load of this call)
+    int rn = kCell * (j0 + 5);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        const unsigned B = ind3(T, st.q0, st.q1, st.q2);            // block b = j0+3+u
+        unsigned B;
+        if ((u & 1) == 0) B = ind3(T, st.qa0, st.qa1, st.qa2); else B = ind3(T, st.qb0, st.qb1, st.qb2);      // block b = j0+3+u
+        unsigned n0, n1, n2;
         if (CLAMP) {
-            st.q0 = gcol[min(rn, hm1) * gp]; st.q1 = gcol[min(rn + 1, hm1) * gp]; st.q2 = gcol[min(rn + 2, hm1) * gp];
+            n0 = gcol[min(rn, hm1) * gp]; n1 = gcol[min(rn + 1, hm1) * gp]; n2 = gcol[min(rn + 2, hm1) * gp];
             rn += kCell;
         } else {
-            st.q0 = pr[0]; st.q1 = pr[gp]; st.q2 = pr[2 * gp];
+            n0 = pr[0]; n1 = pr[gp]; n2 = pr[2 * gp];
             pr += kCell * gp;
         }
+        if ((u & 1) == 0) { st.qa0 = n0; st.qa1 = n1; st.qa2 = n2; } else { st.qb0 = n0; st.qb1 = n1; st.qb2 = n2; }
+        *csp = st.pS + st.p1 + st.p2;                               // lanes that lead no cell write the dummy slot
+        csp += P;
         const int slot = (6 + u) & 7, old = (7 + u) & 7;
         st.S += B - st.r[old];
         st.r[slot] = B;
-        const unsigned s1 = __shfl_down_sync(kFull, st.S, 1), s2 = __shfl_down_sync(kFull, st.S, 2);
-        *csp = st.S + s1 + s2;                                      // lanes that lead no cell write the dummy slot
-        csp += P;
+        st.pS = st.S;
+        st.p1 = __shfl_down_sync(kFull, st.S, 1); st.p2 = __shfl_down_sync(kFull, st.S, 2);
     }
 }
 
@@ -280,7 +310,7 @@ __device__ __forceinline__ bool rank_otsu_aside(const Geom& g) {
 // joins at the final barrier only; else it runs the scan here after its columns.  *otsu_t holds the threshold on return.
 template <class PT>
 VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, const unsigned* hist, int npix,
-                         double* ows, int olast, int* otsu_t, bool oside, PT& pt) {
+                         double* ows, volatile const int* olast, int* otsu_t, bool oside, PT& pt) {
     const int lane = lane_id(), warp = warp_id();
     const int nly = w.nly, nlx = w.nlx;
     const int hm1 = g.h - 1, wm1 = g.w - 1;
@@ -316,19 +346,21 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
                     st.S += B;
                     st.r[3 + bb] = B;
                 }
-                st.q0 = gcol[min(9, hm1) * gp]; st.q1 = gcol[min(10, hm1) * gp]; st.q2 = gcol[min(11, hm1) * gp];
+                st.qa0 = gcol[min(9, hm1) * gp]; st.qa1 = gcol[min(10, hm1) * gp]; st.qa2 = gcol[min(11, hm1) * gp];
+                st.qb0 = gcol[min(12, hm1) * gp]; st.qb1 = gcol[min(13, hm1) * gp]; st.qb2 = gcol[min(14, hm1) * gp];
+                st.pS = st.p1 = st.p2 = 0;
             }
+            csp -= P;                                            // row -1: the first deferred store is empty
             for (int it = 0; it < nit; ++it) {
                 const int j0 = 8 * it;
-                if (kCell * (j0 + 8 + 3) + 2 <= hm1) v_oct<false>(st, T, gcol, gp, hm1, j0, csp, P);
+                if (kCell * (j0 + 12) + 2 <= hm1) v_oct<false>(st, T, gcol, gp, hm1, j0, csp, P);
                 else v_oct<true>(st, T, gcol, gp, hm1, j0, csp, P);
                 csp += 8 * P;
             }
+            *csp = st.pS + st.p1 + st.p2;                        // the last row
         }
         if (owarp) {                                             // (not aside: the scan follows this warp's columns)
-            OtsuJob job;
-            otsu_begin(job, hist, npix, ows, olast);
-            const int t = otsu_end(job);
+            const int t = otsu_scan(hist, npix, ows, olast, pt);
             if (lane == 0) *otsu_t = t;
         }
         if (oside) workers_sync(kThreads - 32); else cta_sync();
@@ -359,6 +391,7 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
                          unsigned* clist, int ccap, PT& pt) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const int hm1 = g.h - 1, wm1 = g.w - 1;
+    pt.acc(35);
     // ---- dirty cells that touch the ROI: listed (they cluster along the plate edge: whole tasks of them), then
     // classified per pixel one cell per thread.  `clist` / `ccap`: a list in shared memory; what does not fit is
     // classified on the spot.
@@ -406,6 +439,7 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
             }
         }
         cta_sync();
+        pt.acc(36);
         const int nlist = min(w.counters[0], ccap);
         for (int k = tid; k < nlist; k += kThreads) {
             const unsigned e = clist[k];

@@ -293,6 +293,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             for (int i = tid; i < plan.n_hist * (kHistWords / 4); i += kThreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         if (tid < 256) sh.hist[tid] = 0;
+        if (tid == 0) sh.otsu_last = -1;              // "no bound yet" for the exact Otsu scan (vi_pipeline.cuh: otsu_scan)
         cta_sync();
         pt.acc(30);
         if (SPEC || (src_mode == 1 && plan.n_hist >= kWarps / 2)) {
@@ -330,7 +331,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         if (warp_id() == 0) {                       // one warp, no barriers in between: approximate threshold, levels, tables
             int last;
             const int ta = otsu_approx_warp(sh.hist, npix, last);
-            if (lane_id() == 0) { sh.t_apx = ta; sh.otsu_last = last; }
+            if (lane_id() == 0) { sh.t_apx = ta; *const_cast<volatile int*>(&sh.otsu_last) = last; }
             pt.acc(33);
             if (lattice && !vote) {
                 select_levels(sh, npix, a.p.threshold, ta, false);
@@ -338,11 +339,9 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             }
             pt.acc(34);
         } else if (oside && warp_id() == kOtsuWarp) {
-            int last;
-            otsu_approx_warp(sh.hist, npix, last);  // (the same bound warp 0 derives: no hand-over to wait for)
-            OtsuJob job;
-            otsu_begin(job, sh.hist, npix, ows, last);
-            const int t = otsu_end(job);
+            long long c0 = pt.stamp();
+            const int t = otsu_scan(sh.hist, npix, ows, &sh.otsu_last, pt);      // (warp 0 publishes the bound meanwhile)
+            pt.lap(37, c0);
             if (lane_id() == 0) sh.otsu_t = t;
         } else if (lattice) {
             rank_cmm(gray, g, rw, 1, oside ? kWarps - 1 : kWarps);     // the cells' gray min / max need no level: meanwhile
@@ -370,12 +369,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         if (oside) { if (warp_id() != kOtsuWarp) workers_sync(kThreads - 32); } else cta_sync();
         if (lattice) {
             pt.tick();   // 2 approximate threshold, levels, tables
-            rank_cells(gray, g, rw, sh.levels, sh.hist, npix, ows, sh.otsu_last, &sh.otsu_t, oside, pt);
+            rank_cells(gray, g, rw, sh.levels, sh.hist, npix, ows, &sh.otsu_last, &sh.otsu_t, oside, pt);
         } else {
             if (warp_id() == kOtsuWarp) {
-                OtsuJob job;
-                otsu_begin(job, sh.hist, npix, ows, sh.otsu_last);
-                const int t = otsu_end(job);
+                const int t = otsu_scan(sh.hist, npix, ows, &sh.otsu_last, pt);
                 if (lane_id() == 0) sh.otsu_t = t;
             }
             cta_sync();
@@ -559,7 +556,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             int y, c; word_rc(g, i, y, c);
             while (q) {
                 const int bpos = __ffs(q) - 1; q &= q - 1;
-                if (rank_exact_pixel_thread(gray, g, thr, c * 32 + bpos, y)) add |= 1u << bpos;
+                if (rank_exact_pixel_thread(gray, g.gp, g.w, g.h, thr, c * 32 + bpos, y)) add |= 1u << bpos;
             }
             MC[i] = add;
         }
