@@ -313,7 +313,25 @@ VI_PHASE bool flood_border_background(const unsigned* M, unsigned* R, const Geom
             }
             changed |= diff != 0u;
         }
-        if (!cta_sync_or(round == 0 ? 1 : changed)) return true;
+        if (round == 0) {
+            // The seeds' rows usually reach everything at once (a plate in a bright field: every background row
+            // runs in from the border).  Checked word-parallel instead of by a second serial round: converged iff
+            // no unreached background pixel has a reached 4-neighbour.
+            cta_sync();
+            int grow = 0;
+            for (int i = threadIdx.x; i < g.nwords; i += kThreads) {
+                int y, c; word_rc(g, i, y, c);
+                const unsigned r = R[i];
+                const unsigned unre = ~M[i] & row_mask_of(g, c) & ~r;
+                if (unre) {
+                    const unsigned lw = c > 0 ? R[i - 1] : 0u, rw = c < g.wpr - 1 ? R[i + 1] : 0u;
+                    const unsigned up = y > 0 ? R[i - g.wpr] : 0u, dn = y < g.h - 1 ? R[i + g.wpr] : 0u;
+                    const unsigned nb = (r << 1) | (lw >> 31) | (r >> 1) | (rw << 31) | up | dn;
+                    grow |= (unre & nb) != 0u;
+                }
+            }
+            if (!cta_sync_or(grow)) return true;
+        } else if (!cta_sync_or(changed)) return true;
     }
     return false;
 }

@@ -224,6 +224,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     unsigned* MC = reinterpret_cast<unsigned*>(Rg + 2 * plan.mask_bytes);
     unsigned* MD = reinterpret_cast<unsigned*>(Rg + 3 * plan.mask_bytes);
     unsigned* ME = reinterpret_cast<unsigned*>(Rg + 4 * plan.mask_bytes);
+    unsigned* CAND = MC;                 // candidate mask of the median stage (ME when it could be zeroed early)
     unsigned char* WS = Rg + kNumMasks * plan.mask_bytes;
 
     // per-CTA global scratch: [u16 hsum][u8 blurred][run-table overflow]
@@ -396,6 +397,12 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             cta_sync();
             pt.tick();   // 4 threshold
+            if (lattice && mode == MODE_FULL && cfg_defect_method == 0) {
+                // the median stage's candidate mask collects bits with atomics: it is zeroed here, where a barrier
+                // follows anyway (ME is free from the threshold's list until the contour filter)
+                for (int i = tid; i < g.nwords; i += kThreads) ME[i] = 0;
+                CAND = ME;
+            }
             // ---- P4: close, open --------------------------------------------------
             if (cfg_se_k == 3) {
                 cross3_pass<false>(MA, MB, g); cta_sync();
@@ -444,7 +451,8 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
                 if (a.n_excl > 0) { apply_exclusions(MA, g, a.excl, a.n_excl, dx, dy); cta_sync(); }
             }
             // ---- P8: seg mask out -------------------------------------------------
-            seg_area = cta_popcount(cta, MA, g);
+            if (mode == MODE_FULL && rs.solid && a.n_excl == 0) seg_area = rs.area;      // one solid blob, untouched since the row scan: its area is the mask's
+            else seg_area = cta_popcount(cta, MA, g);
             if (cfg_seg_stats) mask_sums(cta, MA, g, cfg_seg_stats + (long long)uid * 3);     // CSV export's mask_stats, optional
             if (seg_out) store_mask_bytes(MA, g, seg_out);
             if (cfg_seg_bits) store_mask_words(MA, g, bits_at(cfg_seg_bits));
@@ -538,11 +546,13 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         for (int k = 0; k < 2; ++k) pt.tick();   // 11, 12 (the residual path's slots)
     } else {
     // ---- P11: median residual (second part: the dirty cells against the ROI) ------------
-    for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
-    cta_sync();
+    if (CAND == MC) {
+        for (int i = tid; i < g.nwords; i += kThreads) MC[i] = 0;
+        cta_sync();
+    }
     if (SPEC || lattice) {
         RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
-        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, MC, reinterpret_cast<unsigned*>(WS), min(plan.ws_bytes >> 2, 4096), pt);
+        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, CAND, reinterpret_cast<unsigned*>(WS), min(plan.ws_bytes >> 2, 4096), pt);
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
@@ -566,7 +576,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     pt.tick();   // 11 dirty cells + exact counts
     // ---- P12: open with the 3x3 cross -----------------------------------------
     // (MD, the ROI, is free again; MA may already be receiving the next unit's rows)
-    cross3_pass<true>(MC, MD, g); cta_sync();
+    cross3_pass<true>(CAND, MD, g); cta_sync();
     cross3_pass<false>(MD, MB, g);
     for (int i = tid; i < g.nwords; i += kThreads) any_resid |= (MD[i] != 0);       // erosion result non-empty <=> opening non-empty
     any_resid = cta_sync_or(any_resid);
