@@ -7,6 +7,7 @@
 // call site it reproduces (paths under the reference tree).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "../../include/vi_b200.h"
 
@@ -271,11 +272,13 @@ struct Cta {
 // Diagnostics: per-phase SM cycle counts of one unit (thread 0, after the barrier
 // that ends the phase), written only when KArgs::prof is set.
 constexpr int kProfSlots = 48;
+#define ON_PROF(pt) (std::remove_reference_t<decltype(pt)>::kOn)
 struct PtState { long long* out; long long t; int k; int pad; };      // lives in shared memory: no registers held across phases
 // ON = false compiles every hook away (the production kernel); ON = true is the diagnostics kernel that
 // vi_debug_set_profile selects.
 template <bool ON>
 struct PhaseTimerT {
+    static constexpr bool kOn = ON;
     PtState* s;
     __device__ __forceinline__ void start(PtState* st, long long* o) {
         if (!ON) return;
@@ -287,7 +290,7 @@ struct PhaseTimerT {
         if (threadIdx.x == 0 && s->out) {
             const long long n = clock64();
             const int k = s->k;
-            if (k < kProfSlots) s->out[k] += n - s->t;
+            if (k < kProfSlots) atomicAdd(reinterpret_cast<unsigned long long*>(s->out + k), (unsigned long long)(n - s->t));      // (a reduction: nothing waits for it)
             s->k = k + 1; s->t = n;
         }
     }
@@ -296,14 +299,14 @@ struct PhaseTimerT {
     __device__ __forceinline__ long long lap(int slot, long long c0) {
         if (!ON) return 0ll;
         const long long n = clock64();
-        if ((threadIdx.x & 31) == 0 && s->out) s->out[slot] += n - c0;
+        if ((threadIdx.x & 31) == 0 && s->out) atomicAdd(reinterpret_cast<unsigned long long*>(s->out + slot), (unsigned long long)(n - c0));
         return n;
     }
-    __device__ __forceinline__ void count(int slot, int v) { if (ON && (threadIdx.x & 31) == 0 && s->out) s->out[slot] += v; }
+    __device__ __forceinline__ void count(int slot, int v) { if (ON && (threadIdx.x & 31) == 0 && s->out) atomicAdd(reinterpret_cast<unsigned long long*>(s->out + slot), (unsigned long long)v); }
     // sub-phase accounting: add the time since the last tick/acc to `slot` without consuming a phase slot
     __device__ __forceinline__ void acc(int slot) {
         if (!ON) return;
-        if (threadIdx.x == 0 && s->out) { const long long n = clock64(); s->out[slot] += n - s->t; s->t = n; }
+        if (threadIdx.x == 0 && s->out) { const long long n = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(s->out + slot), (unsigned long long)(n - s->t)); s->t = n; }
     }
 };
 

@@ -175,6 +175,12 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
     }
 }
 
+// (cold: a dirty cell found when the shared list is full)
+__device__ __noinline__ void rank_dirty_cell_cold(const uint8_t* gray, Geom g, int thr, const unsigned* ROI, unsigned* CAND, RankWs w,
+                                                  int ci, int cj, unsigned cw) {
+    rank_dirty_cell(gray, g, thr, ROI, CAND, w, ci, cj, cw);
+}
+
 // M: gray min / max of every cell, four cells (12 pixels = three gray words) per thread and step: the three rows are
 // reduced field-parallel on (even bytes, odd bytes) halves, then each cell's three columns.  Rows past the crop repeat
 // the last row; words past the crop's last word repeat it (their bytes past the crop edge hold in-crop pixels or stale
@@ -402,9 +408,11 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
             unsigned wd[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) { const int t = t0 + q * kThreads + tid; wd[q] = t < ntask ? w.plane[t] : 0u; }      // four loads in flight
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned word = wd[q];
+            if (ON_PROF(pt)) { if ((wd[0] | wd[1] | wd[2] | wd[3]) == 0x12345678u) wd[0] ^= 1u; pt.acc(44); }
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {                             // rolled (the words rotate through wd[0]): cold, branchy code
+                const unsigned word = wd[0];
+                wd[0] = wd[1]; wd[1] = wd[2]; wd[2] = wd[3];
                 unsigned d = word >> 24;
                 if (!d) continue;
                 const int t = t0 + q * kThreads + tid;
@@ -413,31 +421,31 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
                 const int j = rb * 16 + (t & 15);
                 // ROI bits of the 18-pixel strip of the task's cells, three rows OR-ed, then one bit per cell
                 const int x0 = kCell * kGrp * gi, c0 = x0 >> 5, sh = x0 & 31;
+                const int c1 = min(c0 + 1, g.wpr - 1);
+                const unsigned keep1 = c0 + 1 < g.wpr ? 0xffffffffu : 0u;
                 unsigned b = 0;
 #pragma unroll
                 for (int rr = 0; rr < kCell; ++rr) {
-                    const int y = kCell * j + rr;
-                    if (y <= hm1) {
-                        const unsigned* row = ROI + y * g.wpr;
-                        const unsigned lo = row[c0], hi = c0 + 1 < g.wpr ? row[c0 + 1] : 0u;
-                        b |= __funnelshift_r(lo, hi, sh);
-                    }
+                    const unsigned* row = ROI + min(kCell * j + rr, hm1) * g.wpr;      // (a row past the crop repeats the last: its cells' pixels are re-tested one by one)
+                    b |= __funnelshift_r(row[c0], row[c1] & keep1, sh);
                 }
                 b |= (b >> 1) | (b >> 2);                                   // bit 3k: any pixel of cell k
                 const unsigned cells = (b & 1u) | ((b >> 2) & 2u) | ((b >> 4) & 4u) | ((b >> 6) & 8u) | ((b >> 8) & 16u) | ((b >> 10) & 32u);
                 d &= cells;
                 if (!d) continue;
+                pt.count(46, 1);
                 const int nc = __popc(d);
                 int k = atomicAdd(&w.counters[0], nc);
                 while (d) {
                     const int m = __ffs(d) - 1; d &= d - 1;
                     const unsigned code = (word >> (4 * m)) & 15u;
                     if (k < ccap) clist[k] = ((unsigned)j << 16) | ((unsigned)(kGrp * gi + m) << 4) | code;
-                    else rank_dirty_cell(gray, g, thr, ROI, CAND, w, kGrp * gi + m, j, rank_code_thresholds(lv, thr, (int)code));
+                    else rank_dirty_cell_cold(gray, g, thr, ROI, CAND, w, kGrp * gi + m, j, rank_code_thresholds(lv, thr, (int)code));
                     ++k;
                 }
             }
         }
+        pt.acc(45);
         cta_sync();
         pt.acc(36);
         const int nlist = min(w.counters[0], ccap);
