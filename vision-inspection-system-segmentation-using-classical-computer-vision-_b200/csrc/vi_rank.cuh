@@ -186,17 +186,18 @@ __device__ __noinline__ void rank_dirty_cell_cold(const uint8_t* gray, Geom g, i
 // the last row; words past the crop's last word repeat it (their bytes past the crop edge hold in-crop pixels or stale
 // ones: a superset can only turn a clean cell dirty, never the reverse, and dirty cells are classified per pixel).
 // Runs on the warps first_warp .. end_warp-1.
-VI_PHASE void rank_cmm(const uint8_t* gray, const Geom& g, const RankWs& w, int first_warp, int end_warp) {
+// Lattice rows [j_begin, j_end).
+VI_PHASE void rank_cmm(const uint8_t* gray, const Geom& g, const RankWs& w, int first_warp, int end_warp, int j_begin, int j_end) {
     const int nth = (end_warp - first_warp) * 32;
     const int t0 = (int)threadIdx.x - first_warp * 32;
-    if (t0 < 0 || t0 >= nth) return;
+    if (t0 < 0 || t0 >= nth || j_end <= j_begin) return;
     const int hm1 = g.h - 1, wq = g.gp >> 2, nqm1 = ((g.w + 3) >> 2) - 1;
     const int nquad = (w.nlx + 3) >> 2;
-    const int ntask = nquad * w.nly;
+    const int ntask = nquad * (j_end - j_begin);
     const unsigned mq = magic_of((unsigned)nquad);
     const unsigned* gw = reinterpret_cast<const unsigned*>(gray);
     for (int e = t0; e < ntask; e += nth) {
-        const int j = (int)magic_div((unsigned)e, (unsigned)nquad, mq), q = e - j * nquad;
+        const int jr = (int)magic_div((unsigned)e, (unsigned)nquad, mq), q = e - jr * nquad, j = j_begin + jr;
         const int k0 = min(3 * q, nqm1), k1 = min(3 * q + 1, nqm1), k2 = min(3 * q + 2, nqm1);
         const unsigned* r0 = gw + (kCell * j) * wq;
         const unsigned* r1 = gw + min(kCell * j + 1, hm1) * wq;
@@ -311,6 +312,20 @@ __device__ __forceinline__ bool rank_otsu_aside(const Geom& g) {
     return kOtsuWarp * rank_cpw(nslot) >= nslot;
 }
 
+// The warps that own no column of the V pass (and do not run the Otsu scan) take the last lattice rows of the cell
+// min / max pass during it: [rank_cmm_split, nly); the caller runs the rows before the split next to the level selection.
+__device__ __forceinline__ int rank_v_warps(const Geom& g) {
+    const int nslot = rank_nlx(g.w) + 2 * kVPad;
+    const int cpw = rank_cpw(nslot);
+    return min(kWarps, (nslot + cpw - 1) / cpw);
+}
+__device__ __forceinline__ int rank_cmm_split(const Geom& g, bool oside) {
+    const int nly = (g.h + kCell - 1) / kCell;
+    const int idle = (oside ? kWarps - 1 : kWarps) - rank_v_warps(g);
+    if (idle <= 0 || rank_nlx(g.w) + 2 * kVPad > kWarps * rank_cpw(rank_nlx(g.w) + 2 * kVPad)) return nly;      // (several V rounds: no idle warp)
+    return nly * 42 / (42 + 10 * idle);          // 14 warps for about 3 k cycles before, `idle` warps for about 10 k during the V pass
+}
+
 // Part 1 (needs only the gray crop and the levels; the caller has run rank_cmm): window counts on the lattice, the
 // plane of dirty cells.  `oside`: the warp kOtsuWarp is busy with the exact Otsu scan (started by the caller) and
 // joins at the final barrier only; else it runs the scan here after its columns.  *otsu_t holds the threshold on return.
@@ -325,6 +340,10 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
     const int nround = (nslot + kWarps * cpw - 1) / (kWarps * cpw);
     const bool owarp = warp == kOtsuWarp;
     if (!(oside && owarp)) {
+        {
+            const int vw = rank_v_warps(g);
+            rank_cmm(gray, g, w, vw, oside ? kWarps - 1 : kWarps, rank_cmm_split(g, oside), nly);      // idle in the V pass: the rest of the cell min / max
+        }
         const unsigned T = (unsigned)(lv[0] + 512) | ((unsigned)(lv[1] + 512) << 10) | ((unsigned)(lv[2] + 512) << 20);
         int P = w.P, gp = g.gp;
         asm volatile("" : "+r"(P), "+r"(gp));                    // opaque strides (else re-derived from the unit width per store)
@@ -376,6 +395,7 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
             const int nhw = w.nrb * w.ngrp;
             const unsigned mr = magic_of((unsigned)w.nrb);
             const int nhalf = (oside ? kThreads - 32 : kThreads) / 16;
+#pragma unroll 2
             for (int hb = (int)(threadIdx.x >> 4); hb < nhw; hb += nhalf) {
                 const int gi = (int)magic_div((unsigned)hb, (unsigned)w.nrb, mr), rb = hb - gi * w.nrb;
                 const int j = rb * 16 + (int)(threadIdx.x & 15);
@@ -394,9 +414,10 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
 // Returns the number of pixels that needed an exact rank count.
 template <class PT>
 VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int* lv, int thr, const unsigned* ROI, unsigned* CAND,
-                         unsigned* clist, int ccap, PT& pt) {
+                         unsigned* clist, int ccap, unsigned* elist, int ecap, PT& pt) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const int hm1 = g.h - 1, wm1 = g.w - 1;
+    w.exact = elist; w.exact_cap = ecap;                      // the ambiguous-pixel list sits in shared memory too
     pt.acc(35);
     // ---- dirty cells that touch the ROI: listed (they cluster along the plate edge: whole tasks of them), then
     // classified per pixel one cell per thread.  `clist` / `ccap`: a list in shared memory; what does not fit is
@@ -510,30 +531,49 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
             if (ca <= 220 || cb >= 221) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
         }
     } else
-    for (int k2 = warp; k2 < ne; k2 += kWarps) {
-        const unsigned ent = w.exact[k2];
-        const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-        const int gv = gray[y * g.gp + x];
-        const int pa = gv + thr, pb = gv - thr - 1;
-        int vals[14];
+    {
+        // lane's 14 window positions e = lane + 32k -> (dy, dx) = (e / 21, e % 21), as offsets from the window's corner
+        int off[14];
+        int dyx[14];
+        const int gp = g.gp;
 #pragma unroll
         for (int k = 0; k < 14; ++k) {
             const int e = lane + 32 * k;
-            const int dy = e / 21, dx = e - dy * 21;
-            const int yy = min(max(y + dy - 10, 0), hm1), xx = min(max(x + dx - 10, 0), wm1);
-            vals[k] = e < 441 ? (int)gray[yy * g.gp + xx] : 256;
+            const int dy = (e * 3121) >> 16, dx = e - dy * 21;         // e / 21 for e < 448
+            off[k] = dy * gp + dx;
+            dyx[k] = (dy << 8) | dx;
         }
-        unsigned ca = 0, cb = 0;
+        const bool tail = lane + 32 * 13 < 441;                         // the 14th position exists for lanes 0..24
+        for (int k2 = warp; k2 < ne; k2 += kWarps) {
+            const unsigned ent = w.exact[k2];
+            const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+            const int gv = gray[y * gp + x];
+            const int pa = gv + thr, pb = gv - thr - 1;
+            unsigned ca = 0, cb = 0;
+            if (x >= 10 && x + 10 <= wm1 && y >= 10 && y + 10 <= hm1) {  // the window lies inside the crop (uniform over the warp)
+                const uint8_t* corner = gray + (y - 10) * gp + (x - 10);
+                int vals[14];
 #pragma unroll
-        for (int k = 0; k < 14; ++k) { ca += vals[k] <= pa; cb += vals[k] <= pb; }
-        ca = __reduce_add_sync(kFull, ca);
-        cb = __reduce_add_sync(kFull, cb);
-        if (lane == 0 && (ca <= 220 || cb >= 221)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+                for (int k = 0; k < 13; ++k) vals[k] = corner[off[k]];
+                vals[13] = tail ? (int)corner[off[13]] : 256;
+#pragma unroll
+                for (int k = 0; k < 14; ++k) { ca += vals[k] <= pa; cb += vals[k] <= pb; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 14; ++k) {
+                    const int dy = dyx[k] >> 8, dx = dyx[k] & 255;
+                    const int yy = min(max(y + dy - 10, 0), hm1), xx = min(max(x + dx - 10, 0), wm1);
+                    const int v = (k < 13 || tail) ? (int)gray[yy * gp + xx] : 256;
+                    ca += v <= pa; cb += v <= pb;
+                }
+            }
+            ca = __reduce_add_sync(kFull, ca);
+            cb = __reduce_add_sync(kFull, cb);
+            if (lane == 0 && (ca <= 220 || cb >= 221)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+        }
     }
     cta_sync();
-    const int total = w.counters[2];
-    cta_sync();
-    return total;
+    return w.counters[2];          // (the counters are next written after the next unit's histogram: barriers in between)
 }
 
 }  // namespace vi

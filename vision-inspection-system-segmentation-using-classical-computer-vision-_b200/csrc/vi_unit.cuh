@@ -345,7 +345,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             pt.lap(37, c0);
             if (lane_id() == 0) sh.otsu_t = t;
         } else if (lattice) {
-            rank_cmm(gray, g, rw, 1, oside ? kWarps - 1 : kWarps);     // the cells' gray min / max need no level: meanwhile
+            rank_cmm(gray, g, rw, 1, oside ? kWarps - 1 : kWarps, 0, rank_cmm_split(g, oside));     // the cells' gray min / max need no level: meanwhile
         }
         if (vote) {
             // one sample per mask word: is the mask's class the dark one or the bright one?
@@ -552,7 +552,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     }
     if (SPEC || lattice) {
         RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
-        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, CAND, reinterpret_cast<unsigned*>(WS), min(plan.ws_bytes >> 2, 4096), pt);
+        // lists of the stage in the (free) labelling workspace: dirty cells of the ROI, ambiguous pixels
+        const int lcap = min(plan.ws_bytes >> 3, 4096);
+        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, CAND, reinterpret_cast<unsigned*>(WS), lcap,
+                            reinterpret_cast<unsigned*>(WS) + lcap, lcap, pt);
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
