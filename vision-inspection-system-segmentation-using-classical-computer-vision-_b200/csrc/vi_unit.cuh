@@ -559,8 +559,10 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
+#ifndef VI_NO_ASYNC
             if (nuid < a.n_images * a.n_units)
                 cta.gpending = gather_issue(a, nuid, smem, plan.gray_bytes + plan.mask_bytes, &sh.gather_mbar) ? 1 : 0;
+#endif
         }
     } else {
         // units wider than the column-per-thread pass: exact rank count for every ROI pixel
