@@ -162,7 +162,7 @@ extern "C" int vi_ctx_create(int device, vi_ctx** out) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, vi_unit_kernel<false, false, false>));
-    c->smem_static = ((int)fa.sharedSizeBytes + 15) & ~15;
+    c->smem_static = ((int)fa.sharedSizeBytes + 127) & ~127;       // the dynamic part starts 128-byte aligned (tensor copies land there)
     for (auto& s : c->streams) {
         cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete c; return fail(VI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -577,6 +577,59 @@ static long long scratch_layout(vi_ctx* c, int wmax, int hmax, bool f32_plane) {
     return stride;
 }
 
+// The frames as a tensor map for the kernel's asynchronous crop gather (vi_pipeline.cuh: gather_issue_tma).  The
+// encoder is a driver entry point; it is looked up through the runtime so the library keeps linking against cudart
+// only.  Returns false (a.tma_ok = 0: the kernel falls back to one bulk copy per crop row) when anything does not fit.
+typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmap_encode tmap_encoder() {
+    static PFN_tmap_encode fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmap_encode)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+static bool make_frame_tensor(KArgs& a, const GridState& gs) {
+    a.tma_ok = 0;
+    if (const char* e = getenv("VI_GATHER")) { if (strcmp(e, "rows") == 0) return false; }      // VI_GATHER=rows: the per-row bulk copies
+    PFN_tmap_encode enc = tmap_encoder();
+    if (!enc) return false;
+    // the aligned span of a crop: up to 15 bytes of phase in front; tiles of equal width (a multiple of 16) and whole
+    // boxes of rows (a multiple of 8 high: every box starts 128-byte aligned); the fewest column boxes that fit the staging area
+    const int w16 = (gs.wmax + 15 + 15) & ~15;
+    const int nrb = (gs.hmax + 255) / 256;
+    const int bh = (((gs.hmax + nrb - 1) / nrb) + 7) & ~7;
+    if (bh > 256) return false;
+    int ncb = 0, bw = 0, tile_bytes = 0;
+    for (int n = (w16 + 255) / 256; n <= 4; ++n) {
+        const int b = (((w16 + n - 1) / n) + 15) & ~15;
+        const int t = (b * bh * nrb + 127) & ~127;
+        if (b <= 256 && (long long)n * t <= (long long)gs.plan.gray_bytes + gs.plan.mask_bytes) { ncb = n; bw = b; tile_bytes = t; break; }
+    }
+    if (!ncb) return false;
+    if ((a.row_pitch & 15) || (a.n_images > 1 && (a.image_stride & 15)) || (reinterpret_cast<uintptr_t>(a.frames) & 15)) return false;
+    const long long istride = a.n_images > 1 ? a.image_stride : a.row_pitch * (long long)a.H;
+    cuuint64_t gdim[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n_images};
+    cuuint64_t gstr[2] = {(cuuint64_t)a.row_pitch, (cuuint64_t)istride};
+    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(a.frames), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    a.tma_bw = bw; a.tma_bh = bh; a.tma_ncb = ncb; a.tma_nrb = nrb; a.tma_tile_bytes = tile_bytes;
+    a.tma_ok = 1;
+    return true;
+}
+
 constexpr long long kScratchBudget = 24ll << 30;            // per-CTA scratch + arenas of the large-unit path stay below this
 
 // `slot` selects a private copy of the per-CTA scratch so launches on the internal
@@ -629,6 +682,7 @@ static int launch_units(vi_ctx* c, KArgs& a, const GridState& gs, cudaStream_t s
                 (a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0 &&
                 rank_ws_bytes(gs.wmax, gs.hmax) + kOtsuWsBytes <= (long long)(kNumMasks - 1) * gs.plan.mask_bytes + gs.plan.ws_bytes && gs.plan.n_hist >= kWarps / 2;
     if (spec) { const char* e = getenv("VI_KERNEL"); if (e && strcmp(e, "general") == 0) spec = false; }
+    if (spec) make_frame_tensor(a, gs);
 #ifndef VI_CHECKED
     if (a.prof && spec) vi_unit_kernel<true, true, false><<<nblocks, kThreads, gs.plan.total, stream>>>(a);   // diagnostics build: phase timers
     else

@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <type_traits>
+#include <cuda.h>              // CUtensorMap (type only: the encoder is looked up through the runtime, no libcuda link)
 #include <cuda_runtime.h>
 #include "../../include/vi_b200.h"
 
@@ -243,6 +244,12 @@ struct KArgs {
     long long arena_stride;         //  (gray crop, masks, workspace) for units larger than one SM's shared memory
     long long* prof;                // diagnostics: [n_total][kProfSlots] per-phase cycle counts, or null
     SmemPlan plan;
+    // Asynchronous crop gather through the tensor-memory accelerator (vi_pipeline.cuh: gather_issue_tma): the frames as
+    // a 3-D uint8 tensor (x, y, image); one box = tma_bw x tma_bh pixels, a crop = tma_ncb x tma_nrb boxes that land as
+    // tma_ncb dense tiles of row pitch tma_bw (tma_tile_bytes apart) in the staging area.
+    int tma_ok;
+    int tma_bw, tma_bh, tma_ncb, tma_nrb, tma_tile_bytes;
+    alignas(64) CUtensorMap tmap;
 };
 
 // ---------------------------------------------------------------------------

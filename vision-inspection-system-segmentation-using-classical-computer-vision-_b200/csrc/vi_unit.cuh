@@ -264,7 +264,8 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             // the rows were fetched by the bulk-copy engine while the previous unit finished (gather_issue below)
             mbar_wait(&sh.gather_mbar, cta.gpar);
             pt.acc(32);
-            gather_finish(src, a.row_pitch, g, gray);
+            if (a.tma_ok) gather_finish_tma(a, src, a.row_pitch, g, gray);
+            else gather_finish(src, a.row_pitch, g, gray);
             cta.gpar ^= 1u; cta.gpending = 0;
         } else if (SPEC || ((a.row_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0 && (a.image_stride & 15) == 0))
             load_gray16(src, a.row_pitch, g, gray);
@@ -559,10 +560,9 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
-#ifndef VI_NO_ASYNC
             if (nuid < a.n_images * a.n_units)
-                cta.gpending = gather_issue(a, nuid, smem, plan.gray_bytes + plan.mask_bytes, &sh.gather_mbar) ? 1 : 0;
-#endif
+                cta.gpending = (a.tma_ok ? gather_issue_tma(a, nuid, smem, plan.gray_bytes + plan.mask_bytes, &sh.gather_mbar)
+                                         : gather_issue(a, nuid, smem, plan.gray_bytes + plan.mask_bytes, &sh.gather_mbar)) ? 1 : 0;
         }
     } else {
         // units wider than the column-per-thread pass: exact rank count for every ROI pixel
@@ -637,7 +637,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
 
 template <bool PROF, bool SPEC, bool GMEM>
 __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_constant__ KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];      // (128: destination alignment of the tensor copies)
     __shared__ UnitShared sh_raw;
     // The two shared-memory bases are made opaque once: ptxas otherwise re-derives them (S2UR SR_CgaCtaId + a chain
     // of uniform ops) next to nearly every access instead of holding them, also inside the serial Otsu recurrence.
@@ -655,6 +655,8 @@ __global__ void __launch_bounds__(kThreads, 1) vi_unit_kernel(const __grid_const
         cta_sync();
     }
     unsigned char* base = GMEM ? a.arena + (long long)blockIdx.x * a.arena_stride : smem;
+    if (SPEC && a.tma_ok && (int)blockIdx.x < n_total)           // the first unit's crop arrives the same way as the later ones
+        cta.gpending = gather_issue_tma(a, blockIdx.x, smem, a.plan.gray_bytes + a.plan.mask_bytes, &sh.gather_mbar) ? 1 : 0;
     for (int uid = blockIdx.x; uid < n_total; uid += gridDim.x) {
         process_unit<PROF, SPEC, GMEM>(a, uid, base, smem, sh, cta);
         cta_sync();
