@@ -37,14 +37,14 @@ def config5():
     rec = out['r'][0].cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
     n = len(boxes)
     from vi_b200 import _lib
-    prof = torch.zeros((n, 40), dtype=torch.int64, device="cuda")
+    prof = torch.zeros((n, 48), dtype=torch.int64, device="cuda")      # [units][kProfSlots]
     _lib.check(insp._lib.vi_debug_set_profile(insp._ctx, prof.data_ptr()))
     insp.inspect_batch(d, p); torch.cuda.synchronize()
     _lib.check(insp._lib.vi_debug_set_profile(insp._ctx, None))
     m = prof.cpu().numpy().astype(np.float64).mean(axis=0)
-    names = ["gather", "blur+hist", "approx thr+tables", "cells rest+otsu", "threshold", "close/open", "hole fill", "centroid ccl",
+    names = ["gather", "blur+hist", "wait for cell min/max", "cells rest+otsu", "threshold", "close/open", "hole fill", "centroid ccl",
              "excl+seg out", "erosion", "roi ccl", "dirty+exact", "open3", "defect hole fill", "area filter", "defect out"]
-    sub = {20: "rank V", 21: "rank S+C", 22: "rank classify", 23: "ccl count+scan", 24: "ccl extract", 25: "ccl link", 26: "ccl jump B",
+    sub = {20: "rank V", 21: "rank C", 22: "rank classify", 30: "hist zero", 31: "hist blur3 loop", 33: "warp0 approx thr", 34: "warp0 levels", 36: "finish plane scan", 23: "ccl count+scan", 24: "ccl extract", 25: "ccl link", 26: "ccl jump B",
            27: "ccl unions", 28: "ccl jump D", 29: "thr gray mask"}
     tot = m[:16].sum() + sum(m[k] for k in sub)
     print("  cycles per unit %.0f:" % tot, ", ".join(f"{nm} {m[i]:.0f}" for i, nm in enumerate(names)))

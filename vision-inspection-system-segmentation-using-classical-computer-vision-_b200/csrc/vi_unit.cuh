@@ -554,9 +554,9 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
     if (SPEC || lattice) {
         RankWs rw = rank_ws_carve(Rg + plan.mask_bytes, g, g_rank, a.wmax, a.hmax, sh.rank_cnt);
         // lists of the stage in the (free) labelling workspace: dirty cells of the ROI, ambiguous pixels
-        const int lcap = min(plan.ws_bytes >> 3, 4096);
-        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, CAND, reinterpret_cast<unsigned*>(WS), lcap,
-                            reinterpret_cast<unsigned*>(WS) + lcap, lcap, pt);
+        const int ccap = min(plan.ws_bytes >> 4, 4096), ecap = min((plan.ws_bytes >> 2) - ccap, 16384);
+        n_amb = rank_finish(gray, g, rw, sh.levels, thr, MD, CAND, reinterpret_cast<unsigned*>(WS), ccap,
+                            reinterpret_cast<unsigned*>(WS) + ccap, ecap, pt);
         if (SPEC) {
             // the gray crop (and the first mask) are dead from here on: start the next unit's row copies into them
             const int nuid = uid + (int)gridDim.x;
