@@ -234,43 +234,51 @@ __device__ __forceinline__ unsigned ind3(unsigned T, unsigned q0, unsigned q1, u
     return (lo + 2 * hi) >> 9;
 }
 
-// Column state of the V pass: the sliding 7-block sum, the ring of the last 8 block sums (registers: the loop is
-// unrolled by 8 so every ring index is static), the gray of the next two blocks (loaded two blocks ahead) and the
-// previous block's sum with its two shuffles in flight (stored one block later): a warp issues in order, so every
-// value it waits for was asked for a whole block earlier.
+// V pass, one thread per (cell slot, segment of lattice rows).  A thread owns the three columns of its cell and walks
+// down in 3-row blocks: nine gray bytes per block, their level indicators counted per field by three full adders and
+// two additions, the sliding 7-block sum kept by a ring of block sums (registers: the loop is unrolled by 8 so every
+// ring index is static), one store per block.  No cross-lane traffic: the shared-memory pipe takes about one
+// instruction per two cycles and was this pass's bound with one thread per column (three byte loads, two shuffles
+// and a store per column and block; now ten instructions per cell and block instead of eighteen).  Segments of rows
+// put enough warps on a unit; each warms its ring up with the six blocks above its first row.
 struct VState {
     unsigned S;
     unsigned r[8];
-    unsigned qa0, qa1, qa2, qb0, qb1, qb2;
-    unsigned pS, p1, p2;
+    unsigned q[9];             // gray of the next block (3 rows x 3 columns), loaded one block ahead
 };
 
-// Eight lattice rows j0 .. j0+7 <-> blocks b = j0+3 .. j0+10 (sequence n = b+3, ring slot n & 7).  `csp` points at
-// row j0-1 of the thread's slot: the deferred store of the block before.
+__device__ __forceinline__ unsigned ind9(unsigned T, const unsigned* q) {
+    return ind3(T, q[0], q[1], q[2]) + ind3(T, q[3], q[4], q[5]) + ind3(T, q[6], q[7], q[8]);
+}
+
+// Eight lattice rows j0 .. j0+7 <-> blocks b = j0+3 .. j0+10 (sequence n = b+3, ring slot n & 7).
 template <bool CLAMP>
-__device__ __forceinline__ void v_oct(VState& st, unsigned T, const uint8_t* gcol, int gp, int hm1, int j0, unsigned* csp, int P) {
-    const uint8_t* pr = gcol + (kCell * (j0 + 5)) * gp;            // rows of block j0+5 (the first load of this call)
-    int rn = kCell * (j0 + 5);
+__device__ __forceinline__ void v_oct(VState& st, unsigned T, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int gp, int hm1,
+                                      int j0, unsigned* csp, int P) {
+    int rn = kCell * (j0 + 4);                                     // first row of block j0+4 (the first load of this call)
+    const uint8_t* p0 = c0 + rn * gp;
+    const uint8_t* p1 = c1 + rn * gp;
+    const uint8_t* p2 = c2 + rn * gp;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        unsigned B;
-        if ((u & 1) == 0) B = ind3(T, st.qa0, st.qa1, st.qa2); else B = ind3(T, st.qb0, st.qb1, st.qb2);      // block b = j0+3+u
-        unsigned n0, n1, n2;
+        const unsigned B = ind9(T, st.q);                           // block b = j0+3+u
         if (CLAMP) {
-            n0 = gcol[min(rn, hm1) * gp]; n1 = gcol[min(rn + 1, hm1) * gp]; n2 = gcol[min(rn + 2, hm1) * gp];
+            const int o0 = min(rn, hm1) * gp, o1 = min(rn + 1, hm1) * gp, o2 = min(rn + 2, hm1) * gp;
+            st.q[0] = c0[o0]; st.q[1] = c0[o1]; st.q[2] = c0[o2];
+            st.q[3] = c1[o0]; st.q[4] = c1[o1]; st.q[5] = c1[o2];
+            st.q[6] = c2[o0]; st.q[7] = c2[o1]; st.q[8] = c2[o2];
             rn += kCell;
         } else {
-            n0 = pr[0]; n1 = pr[gp]; n2 = pr[2 * gp];
-            pr += kCell * gp;
+            st.q[0] = p0[0]; st.q[1] = p0[gp]; st.q[2] = p0[2 * gp];
+            st.q[3] = p1[0]; st.q[4] = p1[gp]; st.q[5] = p1[2 * gp];
+            st.q[6] = p2[0]; st.q[7] = p2[gp]; st.q[8] = p2[2 * gp];
+            p0 += kCell * gp; p1 += kCell * gp; p2 += kCell * gp;
         }
-        if ((u & 1) == 0) { st.qa0 = n0; st.qa1 = n1; st.qa2 = n2; } else { st.qb0 = n0; st.qb1 = n1; st.qb2 = n2; }
-        *csp = st.pS + st.p1 + st.p2;                               // lanes that lead no cell write the dummy slot
-        csp += P;
         const int slot = (6 + u) & 7, old = (7 + u) & 7;
         st.S += B - st.r[old];
         st.r[slot] = B;
-        st.pS = st.S;
-        st.p1 = __shfl_down_sync(kFull, st.S, 1); st.p2 = __shfl_down_sync(kFull, st.S, 2);
+        *csp = st.S;                                                // lanes past the last slot write the dummy slot
+        csp += P;
     }
 }
 
@@ -303,27 +311,30 @@ __device__ __forceinline__ unsigned rank_group_cells(const RankWs& w, int j, int
     return word;
 }
 
-// Cells per warp of the V pass: full warps for wide units (the pass is issue bound there); narrow units spread their
-// few columns over all warps instead (latency bound otherwise).
-__device__ __forceinline__ int rank_cpw(int nslot) { return nslot > 64 ? kColsPerWarp / kCell : max((nslot + kWarps - 1) / kWarps, 1); }
-// The warp kOtsuWarp owns no column of the V pass: it can run the exact Otsu scan beside the whole stage.
-__device__ __forceinline__ bool rank_otsu_aside(const Geom& g) {
-    const int nslot = rank_nlx(g.w) + 2 * kVPad;
-    return kOtsuWarp * rank_cpw(nslot) >= nslot;
+// Tasks of the V pass: 32 cell slots x one segment of lattice rows per warp.  Segments (up to four) are chosen so that
+// the tasks fit the warps that are free for them, leaving the Otsu warp out when possible.
+struct VPlan { int nchunk, nseg, seg_rows, ntask; };
+__device__ __forceinline__ VPlan rank_vplan(const Geom& g) {
+    VPlan v;
+    const int nslot = rank_nlx(g.w) + 2 * kVPad, nly = (g.h + kCell - 1) / kCell;
+    v.nchunk = (nslot + 31) >> 5;
+    v.nseg = max(1, min(min(4, (kWarps - 1) / v.nchunk), (nly + 7) >> 3));
+    v.seg_rows = (((nly + v.nseg - 1) / v.nseg) + 7) & ~7;
+    v.nseg = (nly + v.seg_rows - 1) / v.seg_rows;
+    v.ntask = v.nchunk * v.nseg;
+    return v;
 }
+// The warp kOtsuWarp gets no task of the V pass: it can run the exact Otsu scan beside the whole stage.
+__device__ __forceinline__ bool rank_otsu_aside(const Geom& g) { return rank_vplan(g).ntask <= kOtsuWarp; }
 
-// The warps that own no column of the V pass (and do not run the Otsu scan) take the last lattice rows of the cell
+// The warps that get no task of the V pass (and do not run the Otsu scan) take the last lattice rows of the cell
 // min / max pass during it: [rank_cmm_split, nly); the caller runs the rows before the split next to the level selection.
-__device__ __forceinline__ int rank_v_warps(const Geom& g) {
-    const int nslot = rank_nlx(g.w) + 2 * kVPad;
-    const int cpw = rank_cpw(nslot);
-    return min(kWarps, (nslot + cpw - 1) / cpw);
-}
+__device__ __forceinline__ int rank_v_warps(const Geom& g) { return min(kWarps, rank_vplan(g).ntask); }
 __device__ __forceinline__ int rank_cmm_split(const Geom& g, bool oside) {
     const int nly = (g.h + kCell - 1) / kCell;
     const int idle = (oside ? kWarps - 1 : kWarps) - rank_v_warps(g);
-    if (idle <= 0 || rank_nlx(g.w) + 2 * kVPad > kWarps * rank_cpw(rank_nlx(g.w) + 2 * kVPad)) return nly;      // (several V rounds: no idle warp)
-    return nly * 42 / (42 + 10 * idle);          // 14 warps for about 3 k cycles before, `idle` warps for about 10 k during the V pass
+    if (idle <= 0) return nly;
+    return nly * 42 / (42 + 8 * idle);           // 14 warps for about 3 k cycles before, `idle` warps for about 8 k during the V pass
 }
 
 // Part 1 (needs only the gray crop and the levels; the caller has run rank_cmm): window counts on the lattice, the
@@ -336,8 +347,7 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
     const int nly = w.nly, nlx = w.nlx;
     const int hm1 = g.h - 1, wm1 = g.w - 1;
     const int nslot = nlx + 2 * kVPad;                           // cell slots of a row: 3 virtual, the cells, 3 virtual
-    const int cpw = rank_cpw(nslot);
-    const int nround = (nslot + kWarps * cpw - 1) / (kWarps * cpw);
+    const VPlan vp = rank_vplan(g);
     const bool owarp = warp == kOtsuWarp;
     if (!(oside && owarp)) {
         {
@@ -347,42 +357,41 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
         const unsigned T = (unsigned)(lv[0] + 512) | ((unsigned)(lv[1] + 512) << 10) | ((unsigned)(lv[2] + 512) << 20);
         int P = w.P, gp = g.gp;
         asm volatile("" : "+r"(P), "+r"(gp));                    // opaque strides (else re-derived from the unit width per store)
-        const int nit = (nly + 7) >> 3;
-        for (int rd = 0; rd < nround; ++rd) {
-            const int slot0 = (rd * kWarps + warp) * cpw;        // first cell slot of this warp
-            if (slot0 >= nslot) continue;
-            const int vcol = kCell * (slot0 - kVPad) + lane;     // may lie left / right of the crop: replicated border
-            const uint8_t* gcol = gray + min(max(vcol, 0), wm1);
-            const int slot = slot0 + lane / kCell;
-            const bool lead = lane < cpw * kCell && (lane % kCell) == 0 && slot < nslot;
-            unsigned* csp = w.cs + (lead ? slot : P - 1);
-            VI_CHECK(!lead || slot < P - 1, CHK_LATTICE_SLOT);
+        for (int task = warp; task < vp.ntask; task += kWarps) {
+            const int seg = task / vp.nchunk, chunk = task - seg * vp.nchunk;
+            const int j0 = seg * vp.seg_rows, j1 = min(j0 + vp.seg_rows, nly);
+            const int slot = chunk * 32 + lane;
+            const int x0 = kCell * (slot - kVPad);               // may lie left / right of the crop: replicated border
+            const uint8_t* c0 = gray + min(max(x0, 0), wm1);
+            const uint8_t* c1 = gray + min(max(x0 + 1, 0), wm1);
+            const uint8_t* c2 = gray + min(max(x0 + 2, 0), wm1);
+            unsigned* csp = w.cs + j0 * P + (slot < nslot ? slot : P - 1);
+            VI_CHECK(nslot <= P - 1 && j1 <= ((nly + 7) & ~7), CHK_LATTICE_SLOT);
             VState st;
             {
-                // prologue: blocks b = -3 .. 2 (rows above the crop replicate row 0)
-                const unsigned g0 = gcol[0];
-                const unsigned Ba = ind3(T, g0, g0, g0);
-                st.S = 3 * Ba;
-                st.r[0] = st.r[1] = st.r[2] = Ba;
+                // warm-up: blocks b = j0-3 .. j0+2 (rows above the crop replicate row 0), then the gray of block j0+3
+                st.S = 0;
                 st.r[6] = st.r[7] = 0;
 #pragma unroll
-                for (int bb = 0; bb < 3; ++bb) {
-                    const unsigned B = ind3(T, gcol[min(3 * bb, hm1) * gp], gcol[min(3 * bb + 1, hm1) * gp], gcol[min(3 * bb + 2, hm1) * gp]);
+                for (int bb = 0; bb < 6; ++bb) {
+                    const int r0 = kCell * (j0 - 3 + bb);
+                    const int o0 = min(max(r0, 0), hm1) * gp, o1 = min(max(r0 + 1, 0), hm1) * gp, o2 = min(max(r0 + 2, 0), hm1) * gp;
+                    unsigned q[9] = {c0[o0], c0[o1], c0[o2], c1[o0], c1[o1], c1[o2], c2[o0], c2[o1], c2[o2]};
+                    const unsigned B = ind9(T, q);
                     st.S += B;
-                    st.r[3 + bb] = B;
+                    st.r[bb] = B;
                 }
-                st.qa0 = gcol[min(9, hm1) * gp]; st.qa1 = gcol[min(10, hm1) * gp]; st.qa2 = gcol[min(11, hm1) * gp];
-                st.qb0 = gcol[min(12, hm1) * gp]; st.qb1 = gcol[min(13, hm1) * gp]; st.qb2 = gcol[min(14, hm1) * gp];
-                st.pS = st.p1 = st.p2 = 0;
+                const int r0 = kCell * (j0 + 3);
+                const int o0 = min(r0, hm1) * gp, o1 = min(r0 + 1, hm1) * gp, o2 = min(r0 + 2, hm1) * gp;
+                st.q[0] = c0[o0]; st.q[1] = c0[o1]; st.q[2] = c0[o2];
+                st.q[3] = c1[o0]; st.q[4] = c1[o1]; st.q[5] = c1[o2];
+                st.q[6] = c2[o0]; st.q[7] = c2[o1]; st.q[8] = c2[o2];
             }
-            csp -= P;                                            // row -1: the first deferred store is empty
-            for (int it = 0; it < nit; ++it) {
-                const int j0 = 8 * it;
-                if (kCell * (j0 + 12) + 2 <= hm1) v_oct<false>(st, T, gcol, gp, hm1, j0, csp, P);
-                else v_oct<true>(st, T, gcol, gp, hm1, j0, csp, P);
+            for (int j = j0; j < j1; j += 8) {
+                if (kCell * (j + 11) + 2 <= hm1) v_oct<false>(st, T, c0, c1, c2, gp, hm1, j, csp, P);
+                else v_oct<true>(st, T, c0, c1, c2, gp, hm1, j, csp, P);
                 csp += 8 * P;
             }
-            *csp = st.pS + st.p1 + st.p2;                        // the last row
         }
         if (owarp) {                                             // (not aside: the scan follows this warp's columns)
             const int t = otsu_scan(hist, npix, ows, olast, pt);
