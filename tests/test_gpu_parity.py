@@ -677,6 +677,66 @@ def test_ragged_grid_and_unaligned_frames(insp):
                     assert rec[fi, u][k] == o[k], (params, fi, u, k, rec[fi, u][k], o[k])
 
 
+def test_async_gather_variants_agree(insp, monkeypatch):
+    """The default kernel fetches the next unit's crop asynchronously, as tensor-map boxes (cp.async.bulk.tensor) or,
+    with VI_GATHER=rows, as one bulk copy per row; both undo the crop's byte phase (x0 & 15) afterwards.  Units at
+    every byte phase and of several sizes, on 16-byte aligned frames: both variants against the cv2 oracle."""
+    import torch
+    W, H = 1024, 420
+    boxes = [((3 + 37 * i + (i % 16), 8 + 5 * (i % 3), 36, 40), i) for i in range(16)]                   # x0 & 15 takes many values
+    boxes += [((16, 70, 316, 315), 16), ((349, 72, 316, 315), 17), ((680, 75, 300, 200), 18), ((683, 290, 97, 111), 19)]
+    frames = np.stack([synth.make_frame(s, [b for b, _ in boxes], H=H, W=W, inset=5, jitter=2) for s in (31, 32, 33)])
+    d = torch.from_numpy(frames).cuda()
+    outs = []
+    for mode in ("", "rows"):
+        if mode: monkeypatch.setenv("VI_GATHER", mode)
+        else: monkeypatch.delenv("VI_GATHER", raising=False)
+        insp.configure(Grid(boxes=boxes), is_reference=True)
+        rec, seg, dfm = insp.inspect_batch(d)
+        torch.cuda.synchronize()
+        outs.append((rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(3, len(boxes)), seg.cpu().numpy().reshape(3, -1),
+                     dfm.cpu().numpy().reshape(3, -1)))
+    monkeypatch.delenv("VI_GATHER", raising=False)
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    for k in ('otsu_t', 'seg_area', 'roi_area', 'defect_area', 'n_kept', 'status'):
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
+    rec, seg, dfm = outs[0]
+    for fi in range(3):
+        recs, osegs, odefs = R.inspect_frame(frames[fi], boxes, R.Params(), (), None, True)
+        segs = insp.split_masks(seg[fi]); defs = insp.split_masks(dfm[fi])
+        for u, o in enumerate(recs):
+            assert np.array_equal(segs[u], osegs[u]), (fi, u, 'seg')
+            ref = odefs[u] if odefs[u] is not None else np.zeros_like(defs[u])
+            assert np.array_equal(defs[u], ref), (fi, u, 'defect')
+            for k in ('seg_area', 'roi_area', 'defect_area', 'n_kept', 'status'):
+                assert rec[fi, u][k] == o[k], (fi, u, k)
+
+
+def test_detect_defects_on_a_bright_region(insp):
+    """detect_defects takes any mask (indexing_ui.py:1486-1490).  The median stage brackets the median with levels
+    around ONE class of the crop -- the dark one for the path's own inverse-threshold masks, the bright one when the
+    caller's mask lives there (one gray sample per mask word votes).  Either choice is exact; this pins the second."""
+    rng = np.random.default_rng(77)
+    for shape in ((120, 150), (315, 316)):
+        h, w = shape
+        gray = np.clip(60 + rng.normal(0, 5, size=shape), 0, 255).astype(np.uint8)
+        gray[15:h - 15, 15:w - 15] = np.clip(200 + rng.normal(0, 6, size=(h - 30, w - 30)), 0, 255).astype(np.uint8)
+        for _ in range(4):                                               # dark specks on the bright plate
+            cy, cx = int(rng.integers(30, h - 30)), int(rng.integers(30, w - 30))
+            gray[cy - 3:cy + 4, cx - 3:cx + 4] = 90
+        seg = np.zeros(shape, np.uint8); seg[15:h - 15, 15:w - 15] = 255
+        for (r, thr, mn) in ((6, 24, 20), (2, 10, 3)):
+            info = {}
+            ref = R.detect_defects(gray, seg, 'threshold', thr, mn, r, info)
+            got, rec = insp.detect_defects(gray, seg, vi_b200.default_params(threshold=thr, min_area=mn, erode_px=r), return_record=True)
+            assert (ref is None) == (got is None)
+            assert ref is not None and (ref > 0).any()
+            assert np.array_equal(got, ref), (shape, r, thr, int((got != ref).sum()))
+            assert rec["n_kept"] == info["n_kept"]
+            if (r, thr) == (6, 24):
+                assert rec["n_ambiguous"] < 0.2 * (h * w), "the levels did not follow the mask's class"
+
+
 def test_seg_stats_output_matches_mask_stats(insp, golden, tmp_path):
     """The optional per-unit (area, sum x, sum y) of the final seg masks against the reference's
     mask_stats on the masks themselves, and the CSV rows built from it against rows built the reference's way."""
