@@ -277,8 +277,47 @@ constexpr int kFloodRounds = 5;
 
 VI_PHASE bool flood_border_background(const unsigned* M, unsigned* R, const Geom& g) {
     const unsigned lastbit = 1u << ((g.w - 1) & 31);
+    // Round 0, seeds only: the first and last row reach all of their background; every other row the background run
+    // at its left end and the one at its right end (what the carry trick below would make of two end seeds): the words
+    // up to the first foreground pixel from either side, a handful of word steps per row instead of two passes over all.
+    for (int y = threadIdx.x; y < g.h; y += kThreads) {
+        const unsigned* mrow = M + y * g.wpr;
+        unsigned* rrow = R + y * g.wpr;
+        if (y == 0 || y == g.h - 1) {
+            for (int c = 0; c < g.wpr; ++c) rrow[c] = ~mrow[c] & row_mask_of(g, c);
+            continue;
+        }
+        int c = 0;
+        for (; c < g.wpr; ++c) {                                 // from the left
+            const unsigned full = row_mask_of(g, c), b = ~mrow[c] & full;
+            if (b == full) { rrow[c] = b; continue; }
+            const int n = __ffs(~b) - 1;                          // background pixels before the first foreground one (or the row's end)
+            rrow[c] = n ? (0xffffffffu >> (32 - n)) : 0u;
+            break;
+        }
+        if (c >= g.wpr) continue;                                // no foreground in this row: all reached
+        const int cl = c;
+        int cr = g.wpr - 1;
+        for (; cr > cl; --cr) {                                  // from the right, down to the word the left run stopped in
+            const unsigned full = row_mask_of(g, cr), b = ~mrow[cr] & full;
+            if (b == full) { rrow[cr] = b; continue; }
+            const int top = 31 - __clz(full);                     // the row's last pixel in this word
+            const int n = __clz(~b << (31 - top));                // background pixels after the last foreground one
+            rrow[cr] = n ? (full & ~(0xffffffffu >> (31 - top + n))) & full : 0u;
+            break;
+        }
+        if (cr == cl) {                                          // both runs end in the same word
+            const unsigned full = row_mask_of(g, cl), b = ~mrow[cl] & full;
+            const int top = 31 - __clz(full);
+            const int n = __clz(~b << (31 - top));
+            rrow[cl] |= n ? (full & ~(0xffffffffu >> (31 - top + n))) & full : 0u;
+        } else {
+            for (int k = cl + 1; k < cr; ++k) rrow[k] = 0u;      // between the two runs: not reached yet
+        }
+    }
     for (int round = 0; round <= kFloodRounds; ++round) {
         int changed = 0;
+        if (round > 0)
         for (int y = threadIdx.x; y < g.h; y += kThreads) {
             const unsigned* mrow = M + y * g.wpr;
             unsigned* rrow = R + y * g.wpr;
