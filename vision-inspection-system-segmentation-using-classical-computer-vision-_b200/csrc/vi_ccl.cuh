@@ -263,6 +263,39 @@ VI_PHASE RowScan mask_row_scan(Cta& cs, const unsigned* M, const Geom& g, unsign
     return r;
 }
 
+// The same for a mask that flood_border_background has just filled straight from its seeding round (return value 2):
+// then every row but the first and the last is empty or the single run from its first to its last foreground pixel --
+// the extents `info` already holds from the scan before the fill -- so no word is read again (the two edge rows, which
+// the fill leaves as they are, are counted once more to see whether they are single runs).  One barrier.
+VI_PHASE RowScan mask_row_rescan_filled(Cta& cs, const unsigned* M, const Geom& g, const unsigned* info) {
+    RowScan r;
+    r.any_multi = false;
+    unsigned long long area = 0, sx = 0, sy = 0, firsts = 0, bad = 0;
+    for (int y = threadIdx.x; y < g.h; y += kThreads) {
+        const unsigned me = info[y];
+        if (me == 0xffffffffu) continue;
+        const int xs = (int)(me & 0xffffu), xe = (int)(me >> 16);
+        const unsigned n = (unsigned)(xe - xs + 1);
+        if (y == 0 || y == g.h - 1) {
+            unsigned cnt = 0;
+            for (int c = 0; c < g.wpr; ++c) cnt += __popc(M[y * g.wpr + c]);
+            if (cnt != n) bad = 1;                                 // an edge row with several runs: not one solid blob
+        }
+        area += n; sx += (unsigned long long)(xs + xe) * n / 2; sy += (unsigned long long)y * n;
+        const unsigned up = y > 0 ? info[y - 1] : 0xffffffffu;
+        if (up == 0xffffffffu) { ++firsts; continue; }
+        const int pxs = (int)(up & 0xffffu), pxe = (int)(up >> 16);
+        if (!(xs <= pxe + 1 && xe >= pxs - 1)) bad = 1;
+    }
+    unsigned a32 = (unsigned)area;
+    unsigned long long vx = sx | (firsts << 48), vy = sy | (bad << 48);
+    cta_sum3(cs, a32, vx, vy);
+    r.area = a32;
+    r.solid = (vx >> 48) == 1u && (vy >> 48) == 0u;
+    r.sx = vx & 0xffffffffffffull; r.sy = vy & 0xffffffffffffull;
+    return r;
+}
+
 // Hole fill without labelling.  The background that is 4-connected to the crop border is grown directly on the bit
 // rows: one thread owns one row and, per round, seeds it with what is already reached in the row itself and in the
 // rows above and below, then extends every seed to the ends of its background run (an addition ripples a carry
@@ -271,11 +304,11 @@ VI_PHASE RowScan mask_row_scan(Cta& cs, const unsigned* M, const Geom& g, unsign
 // whole first / last row.  Reads of neighbour rows may see a round's old or new words -- both are subsets of the true
 // reachable set, so the iteration is monotone and its fixed point is exact.  A plate with inclusions converges at
 // once; if `kFloodRounds` do not suffice (spirals, long vertical channels) the caller labels the background instead.
-//   M: the mask (foreground);  R: scratch, receives the reached background;  returns true when converged, and then
-//   M | holes == ~R & row mask.
+//   M: the mask (foreground);  R: scratch, receives the reached background;  returns non-zero when converged (2: by the
+//   seeding round alone), and then M | holes == ~R & row mask.
 constexpr int kFloodRounds = 5;
 
-VI_PHASE bool flood_border_background(const unsigned* M, unsigned* R, const Geom& g) {
+VI_PHASE int flood_border_background(const unsigned* M, unsigned* R, const Geom& g) {
     const unsigned lastbit = 1u << ((g.w - 1) & 31);
     // Round 0, seeds only: the first and last row reach all of their background; every other row the background run
     // at its left end and the one at its right end (what the carry trick below would make of two end seeds): the words
@@ -369,10 +402,10 @@ VI_PHASE bool flood_border_background(const unsigned* M, unsigned* R, const Geom
                     grow |= (unre & nb) != 0u;
                 }
             }
-            if (!cta_sync_or(grow)) return true;
-        } else if (!cta_sync_or(changed)) return true;
+            if (!cta_sync_or(grow)) return 2;                    // settled by the seeds alone
+        } else if (!cta_sync_or(changed)) return 1;
     }
-    return false;
+    return 0;
 }
 
 // Warp-aggregated per-root accumulation: lanes whose root equals the first valid

@@ -178,8 +178,10 @@ __device__ inline void write_record(const KArgs& a, int uid, int img, int unit, 
 // two rounds; what it cannot settle in kFloodRounds is labelled (background runs, 4-connectivity, united with the
 // virtual outside node when they touch the border).  Returns the run count of the labelling pass (0: flood).
 template <class PT>
-VI_PHASE int fill_holes(Cta& cta, unsigned* M, unsigned* T, const Geom& g, const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PT* pt) {
-    if (flood_border_background(M, T, g)) {
+VI_PHASE int fill_holes(Cta& cta, unsigned* M, unsigned* T, const Geom& g, const CclWs& ws_s, const CclWs& ws_g, CclWs& ws, PT* pt, int* how = nullptr) {
+    const int fl = flood_border_background(M, T, g);
+    if (how) *how = fl;
+    if (fl) {
         for (int i = threadIdx.x; i < g.nwords; i += kThreads)
             M[i] = ~T[i] & row_mask_of(g, i - (int)magic_div((unsigned)i, (unsigned)g.wpr, g.mwpr) * g.wpr);
         cta_sync();
@@ -421,8 +423,9 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             unsigned* rowinfo = reinterpret_cast<unsigned*>(ws_s.row_first());
             RowScan rs = mask_row_scan(cta, MA, g, rowinfo);
             if (rs.any_multi) {                              // a row with several runs: the background may have holes
-                n_runs_max = max(n_runs_max, fill_holes(cta, MA, MB, g, ws_s, ws_g, ws, &pt));
-                if (mode == MODE_FULL) rs = mask_row_scan(cta, MA, g, rowinfo);
+                int how = 0;
+                n_runs_max = max(n_runs_max, fill_holes(cta, MA, MB, g, ws_s, ws_g, ws, &pt, &how));
+                if (mode == MODE_FULL) rs = how == 2 ? mask_row_rescan_filled(cta, MA, g, rowinfo) : mask_row_scan(cta, MA, g, rowinfo);
             }
             pt.tick();   // 6 hole fill
             if (mode == MODE_FULL) {
