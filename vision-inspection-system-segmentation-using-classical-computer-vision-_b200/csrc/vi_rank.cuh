@@ -463,7 +463,6 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
                 const unsigned cells = (b & 1u) | ((b >> 2) & 2u) | ((b >> 4) & 4u) | ((b >> 6) & 8u) | ((b >> 8) & 16u) | ((b >> 10) & 32u);
                 d &= cells;
                 if (!d) continue;
-                pt.count(46, 1);
                 const int nc = __popc(d);
                 int k = atomicAdd(&w.counters[0], nc);
                 while (d) {

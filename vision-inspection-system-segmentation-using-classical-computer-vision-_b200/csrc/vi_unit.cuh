@@ -395,7 +395,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
                 threshold_gray(gray, g, MB, otsu_t, sh.misc);
                 cta_sync();
                 pt.acc(29);
-                threshold_band(gray, g, MB, MA, MC, otsu_t, MD, 2 * (plan.mask_bytes / 4), sh.misc);
+                threshold_band(gray, g, MB, MA, MC, otsu_t, MD, 2 * (plan.mask_bytes / 4), sh.misc, pt);
             }
             else blur_pass<2, false>(gray, g_blur, g, nullptr, nullptr, 0, kWarps, MA, otsu_t);
             cta_sync();
