@@ -285,7 +285,7 @@ __device__ __forceinline__ void v_oct(VState& st, unsigned T, const uint8_t* c0,
 // C: one task = kGrp consecutive cells of one lattice row.  The window of cell i is the seven cells i-3 .. i+3 = slots
 // i .. i+6 of the row; a thread forms the first window and slides it over the group.  Every load is independent of the
 // others; threads of a half-warp hold 16 consecutive rows (odd row pitch: distinct banks).
-__device__ __forceinline__ unsigned rank_group_cells(const RankWs& w, int j, int gi) {
+__device__ __forceinline__ unsigned rank_group_cells(const RankWs& w, int j, int gi, unsigned u2p, unsigned u3p) {
     const unsigned* row = w.cs + j * w.P + kGrp * gi;
     const unsigned short* cm = w.cmm + j * w.cpitch + kGrp * gi;
     unsigned c[kGrp + 6];
@@ -302,9 +302,10 @@ __device__ __forceinline__ unsigned rank_group_cells(const RankWs& w, int j, int
     for (int m = 0; m < kGrp; ++m) {
         const int n263 = __popc((C + kGe263) & kFlag), n179 = __popc((C + kGe179) & kFlag);
         const unsigned code = (unsigned)(n179 * 4 + n263);
-        const unsigned cw = w.table[code];
+        // the clean range [U2, U3]: U2 follows HI (n263), U3 follows LO (n179) -- a byte pick each, no table load
+        const unsigned U2 = __byte_perm(u2p, 0u, 0x4440u | (unsigned)n263), U3 = __byte_perm(u3p, 0u, 0x4440u | (unsigned)n179);
         const unsigned mn = mmv[m] & 255u, mx = mmv[m] >> 8;
-        const bool dirty = kGrp * gi + m < w.nlx && (mn < ((cw >> 8) & 255u) || mx > ((cw >> 16) & 255u));
+        const bool dirty = kGrp * gi + m < w.nlx && (mn < U2 || mx > U3);
         word |= (code << (4 * m)) | ((dirty ? 1u : 0u) << (24 + m));
         if (m + 1 < kGrp) C += c[m + 7] - c[m];
     }
@@ -404,12 +405,15 @@ VI_PHASE void rank_cells(const uint8_t* gray, const Geom& g, RankWs w, const int
             const int nhw = w.nrb * w.ngrp;
             const unsigned mr = magic_of((unsigned)w.nrb);
             const int nhalf = (oside ? kThreads - 32 : kThreads) / 16;
+            unsigned u2p = 0, u3p = 0;                                // U2 by n263, U3 by n179, four bytes each
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { u2p |= ((w.table[k] >> 8) & 255u) << (8 * k); u3p |= ((w.table[4 * k] >> 16) & 255u) << (8 * k); }
 #pragma unroll 2
             for (int hb = (int)(threadIdx.x >> 4); hb < nhw; hb += nhalf) {
                 const int gi = (int)magic_div((unsigned)hb, (unsigned)w.nrb, mr), rb = hb - gi * w.nrb;
                 const int j = rb * 16 + (int)(threadIdx.x & 15);
                 unsigned word = 0;
-                if (j < nly) word = rank_group_cells(w, j, gi);
+                if (j < nly) word = rank_group_cells(w, j, gi, u2p, u3p);
                 VI_CHECK(hb * 16 + 15 < w.plane_cap, CHK_DIRTY_LIST);
                 w.plane[hb * 16 + (threadIdx.x & 15)] = word;
             }
