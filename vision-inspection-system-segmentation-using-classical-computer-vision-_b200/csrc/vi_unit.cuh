@@ -273,7 +273,7 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
             load_gray16(src, a.row_pitch, g, gray);
         else
             load_gray(src, a.row_pitch, g, gray);
-        if (uid + (int)gridDim.x < a.n_images * a.n_units) prefetch_crop_l2(a, uid + (int)gridDim.x);
+        if (!(SPEC && a.tma_ok) && uid + (int)gridDim.x < a.n_images * a.n_units) prefetch_crop_l2(a, uid + (int)gridDim.x);
         cta_sync();
         pt.tick();   // 0 gather
         // ---- P1: blur + histogram ------------------------------------------------
