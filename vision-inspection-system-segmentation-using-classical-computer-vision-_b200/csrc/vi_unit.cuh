@@ -264,7 +264,8 @@ __device__ __forceinline__ void process_unit(const KArgs& a, int uid, unsigned c
         const uint8_t* src = a.frames + (long long)img * a.image_stride + (long long)rc.y * a.row_pitch + rc.x;
         if (SPEC && cta.gpending) {
             // the rows were fetched by the bulk-copy engine while the previous unit finished (gather_issue below)
-            mbar_wait(&sh.gather_mbar, cta.gpar);
+            if (warp_id() == 0) mbar_wait(&sh.gather_mbar, cta.gpar);      // one warp polls; the barrier hands its acquire on to the rest
+            cta_sync();
             pt.acc(32);
             if (a.tma_ok) gather_finish_tma(a, src, a.row_pitch, g, gray);
             else gather_finish(src, a.row_pitch, g, gray);
