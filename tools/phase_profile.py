@@ -36,7 +36,7 @@ def main():
     rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
     mean = p.mean(axis=0)
     tot = mean[:len(NAMES)].sum()
-    print(f"{n} images, {n*48} units, kernel {e0.elapsed_time(e1):.3f} ms; mean cycles/unit {mean[:37].sum():.0f} (phase slots {tot:.0f} + sub-phase slots {mean[len(NAMES):37].sum():.0f}; slots 37+ run beside them on the Otsu warp)")
+    print(f"{n} images, {n*48} units, kernel {e0.elapsed_time(e1):.3f} ms; mean cycles/unit {mean[:37].sum() + mean[44] + mean[45] + mean[47]:.0f} (phase slots {tot:.0f} + sub-phase slots {mean[len(NAMES):37].sum() + mean[44] + mean[45] + mean[47]:.0f}; slots 37-43 run beside them on the Otsu warp, 46 is a count)")
     for i, nm in enumerate(NAMES):
         print(f"  {i:2d} {nm:18s} {mean[i]:10.0f}  {100*mean[i]/tot:5.1f}%   max {p[:, i].max():10.0f}")
     for i, nm in ((20, "rank: V"), (21, "rank: C"), (22, "rank: classify"), (23, "ccl: count+scan"), (24, "ccl: extract"), (25, "ccl: link"), (26, "ccl: jump B"), (27, "ccl: unions"), (28, "ccl: jump D"), (29, "thr: gray mask"), (30, "hist: zero"), (31, "hist: blur3 loop"), (32, "gather: wait for rows"), (33, "warp0: approx thr"), (34, "warp0: levels+tables"), (35, "finish: zero cand"), (36, "finish: plane scan"), (37, "otsu warp: scan"), (38, "otsu: p, ip"), (39, "otsu: q1 sums"), (40, "otsu: y"), (41, "otsu: chain"), (42, "otsu: sigma, arg max"), (43, "otsu: bins (count)"), (44, "finish: plane loads (thread 0)"), (45, "finish: thread 0 roi tests"), (46, "thr: listed band pixels (count, x16 warps)"), (47, "thr: band pass A")):
