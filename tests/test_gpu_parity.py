@@ -14,7 +14,7 @@ from oracle import ref_cv2 as R
 from oracle import restate as S
 import vi_b200
 from vi_b200 import synth
-from vi_b200.grid import Grid
+from vi_b200.grid import Grid, generate_grid
 
 
 @pytest.fixture(scope="module")
@@ -644,6 +644,35 @@ def test_full_size_batch_properties(insp, golden):
     hrec, hseg, hdef = insp.inspect_batch_host(frames)
     assert np.array_equal(hseg.reshape(64, -1), seg) and np.array_equal(hdef.reshape(64, -1), dfm)
     assert np.array_equal(hrec['status'].reshape(64, nu), rec['status']) and np.array_equal(hrec['image'].reshape(64, nu), rec['image'])
+
+
+def test_config4_full_size_erosion_sweep(insp):
+    """BASELINE configs[3] as stated: the grid.json grid on a full 4096x3000 frame, rectangle + circle exclusions, a
+    per-unit centroid shift against a reference frame (grid JSON v2, indexing_ui.py:2296-2338), erosion radii across
+    1..63 (direct passes up to 10, window doubling above): every unit's masks and record against the cv2 oracle."""
+    import torch
+    boxes = generate_grid((251, 232, 316, 315), 4, 6, 2, 1, 133, 136, 252, 0)
+    frames = np.stack([synth.make_frame(s, [b for b, _ in boxes]) for s in (40, 41)])
+    excl = [{'shape': 'rect', 'x': 50, 'y': 60, 'w': 70, 'h': 30}, {'shape': 'circle', 'cx': 200, 'cy': 180, 'r': 25}]
+    recs0, _, _ = R.inspect_frame(frames[0], boxes, R.Params(), excl, None, True)
+    refc = {i: (r['cx'], r['cy']) for i, r in enumerate(recs0) if r['cx'] == r['cx']}
+    insp.configure(Grid(boxes=boxes, exclusions=excl, ref_centroids=refc), is_reference=False)
+    d = torch.from_numpy(frames[1:2]).cuda()
+    shifted = 0
+    for r in (1, 10, 11, 63):
+        rec, seg, dfm = insp.inspect_batch(d, vi_b200.default_params(erode_px=r))
+        torch.cuda.synchronize()
+        rec = rec.cpu().numpy().view(vi_b200.RECORD_DTYPE).reshape(-1)
+        segs = insp.split_masks(seg.cpu().numpy()); defs = insp.split_masks(dfm.cpu().numpy())
+        recs, osegs, odefs = R.inspect_frame(frames[1], boxes, R.Params(erode_px=r), excl, refc, False)
+        for u, o in enumerate(recs):
+            assert np.array_equal(segs[u], osegs[u]), (r, u, 'seg')
+            ref = odefs[u] if odefs[u] is not None else np.zeros_like(defs[u])
+            assert np.array_equal(defs[u], ref), (r, u, 'defect')
+            for k in ('seg_area', 'roi_area', 'defect_area', 'n_kept', 'status', 'dx', 'dy'):
+                assert rec[u][k] == o[k], (r, u, k, rec[u][k], o[k])
+            shifted += int(o['dx'] != 0 or o['dy'] != 0)
+    assert shifted > 0, "the frames' jitter should shift some centroids"
 
 
 def test_ragged_grid_and_unaligned_frames(insp):
