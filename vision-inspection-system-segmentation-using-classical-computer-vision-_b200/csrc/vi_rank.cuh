@@ -24,7 +24,7 @@
 //    edge, and the defects) are classified per pixel, and ambiguous ROI pixels get an
 //    exact rank count at their own two pivots.  Cells of the bright field are dirty by
 //    construction (no level brackets their median) and are dropped by the ROI test,
-//    24 cells per word operation.
+//    six cells (one task of the C pass) at a time.
 //    Exact for any level set and any image
 //    (oracle/restate.py: residual_mask_lattice is the numpy twin).
 //
