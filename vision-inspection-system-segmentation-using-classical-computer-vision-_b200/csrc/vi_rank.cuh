@@ -57,7 +57,7 @@ struct RankWs {
     unsigned* plane;     // [ntasks] per C task: 6 codes (4 bits each) | 6 dirty bits << 24, in the CTA's global scratch
     unsigned* exact;     // [exact_cap] ambiguous pixels (y << 16 | x), global scratch; more are counted inline
     int exact_cap;
-    int* counters;       // shared: [0] dirty cells in the ROI, [1] ambiguous pixels listed, [2] ambiguous pixels total
+    int* counters;       // shared: [0] dirty cells in the ROI, [1] ambiguous pixels (the first exact_cap of them are listed)
     int P, cpitch, nlx, nly, ngrp, nrb;
     int plane_cap;       // words the plane holds (CHECKED builds)
 };
@@ -150,6 +150,7 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
         any |= roi3[rr];
     }
     if (!any) return;
+    unsigned amb = 0;                                            // ambiguous pixels of the cell, bit rr * 3 + cc
 #pragma unroll
     for (int rr = 0; rr < kCell; ++rr) {
         const int y = cj * kCell + rr;
@@ -158,20 +159,22 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
         for (int cc = 0; cc < kCell; ++cc) {
             const int x = ci * kCell + cc;
             if (x >= g.w) break;
-            const int wi = y * g.wpr + (x >> 5);
-            const unsigned bit = 1u << (x & 31);
             if (!((roi3[rr] >> cc) & 1u)) continue;
             const unsigned gv = gray[y * g.gp + x];
-            if (gv < u1 || gv > u4) {
-                atomicOr(&CAND[wi], bit);
-            } else if (!(gv >= u2 && gv <= u3)) {
-                atomicAdd(&w.counters[2], 1);
-                const int k = atomicAdd(&w.counters[1], 1);
-                VI_CHECK(k >= 0 && y < g.h && x < g.w, CHK_EXACT_LIST);
-                if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | (unsigned)x;
-                else if (rank_exact_pixel_thread(gray, g.gp, g.w, g.h, thr, x, y)) atomicOr(&CAND[wi], bit);
-            }
+            if (gv < u1 || gv > u4) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+            else if (!(gv >= u2 && gv <= u3)) amb |= 1u << (rr * kCell + cc);
         }
+    }
+    if (!amb) return;
+    int k = atomicAdd(&w.counters[1], __popc(amb));              // one reservation per cell (a noisy unit lists thousands of pixels)
+    while (amb) {
+        const int b = __ffs(amb) - 1; amb &= amb - 1;
+        const int rr = b / kCell, cc = b - rr * kCell;
+        const int y = cj * kCell + rr, x = ci * kCell + cc;
+        VI_CHECK(k >= 0 && y < g.h && x < g.w, CHK_EXACT_LIST);
+        if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | (unsigned)x;
+        else if (rank_exact_pixel_thread(gray, g.gp, g.w, g.h, thr, x, y)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+        ++k;
     }
 }
 
@@ -585,7 +588,7 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
         }
     }
     cta_sync();
-    return w.counters[2];          // (the counters are next written after the next unit's histogram: barriers in between)
+    return w.counters[1];          // every ambiguous pixel, listed or not (the counters are next written after the next unit's histogram: barriers in between)
 }
 
 }  // namespace vi
