@@ -150,7 +150,10 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
         any |= roi3[rr];
     }
     if (!any) return;
-    unsigned amb = 0;                                            // ambiguous pixels of the cell, bit rr * 3 + cc
+    // Ambiguous pixels, by the test that is still open (bit rr * 3 + cc): A "more than 220 of the window lie above
+    // g + thr" can only hold below the clean range (g < U2), B "at least 221 lie at or below g - thr - 1" only above it
+    // (g > U3) -- one list entry per open test, so the exact pass counts against ONE pivot per entry.
+    unsigned ambA = 0, ambB = 0;
 #pragma unroll
     for (int rr = 0; rr < kCell; ++rr) {
         const int y = cj * kCell + rr;
@@ -162,19 +165,26 @@ __device__ inline void rank_dirty_cell(const uint8_t* gray, const Geom& g, int t
             if (!((roi3[rr] >> cc) & 1u)) continue;
             const unsigned gv = gray[y * g.gp + x];
             if (gv < u1 || gv > u4) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
-            else if (!(gv >= u2 && gv <= u3)) amb |= 1u << (rr * kCell + cc);
+            else {
+                if (gv < u2) ambA |= 1u << (rr * kCell + cc);
+                if (gv > u3) ambB |= 1u << (rr * kCell + cc);
+            }
         }
     }
-    if (!amb) return;
-    int k = atomicAdd(&w.counters[1], __popc(amb));              // one reservation per cell (a noisy unit lists thousands of pixels)
-    while (amb) {
-        const int b = __ffs(amb) - 1; amb &= amb - 1;
-        const int rr = b / kCell, cc = b - rr * kCell;
-        const int y = cj * kCell + rr, x = ci * kCell + cc;
-        VI_CHECK(k >= 0 && y < g.h && x < g.w, CHK_EXACT_LIST);
-        if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | (unsigned)x;
-        else if (rank_exact_pixel_thread(gray, g.gp, g.w, g.h, thr, x, y)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
-        ++k;
+    if (!(ambA | ambB)) return;
+    int k = atomicAdd(&w.counters[1], __popc(ambA) + __popc(ambB));      // one reservation per cell (a noisy unit lists thousands)
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+        unsigned amb = t ? ambB : ambA;
+        while (amb) {
+            const int b = __ffs(amb) - 1; amb &= amb - 1;
+            const int rr = b / kCell, cc = b - rr * kCell;
+            const int y = cj * kCell + rr, x = ci * kCell + cc;
+            VI_CHECK(k >= 0 && y < g.h && x < g.w && x < 0x8000, CHK_EXACT_LIST);
+            if (k < w.exact_cap) w.exact[k] = ((unsigned)y << 16) | ((unsigned)t << 15) | (unsigned)x;
+            else if (rank_exact_pixel_thread(gray, g.gp, g.w, g.h, thr, x, y)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+            ++k;
+        }
     }
 }
 
@@ -502,34 +512,33 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
         const int gp = g.gp;
         for (int k2 = tid; k2 < ne; k2 += kThreads) {
             const unsigned ent = w.exact[k2];
-            const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+            const int y = (int)(ent >> 16), x = (int)(ent & 0x7fffu);
+            const bool tb = (ent >> 15) & 1u;                        // which test: B counts against g - thr - 1, A against g + thr
             const int gv = gray[y * gp + x];
-            const int pa = gv + thr, pb = gv - thr - 1;
-            int ca = 0, cb = 0;
+            const int pv = tb ? gv - thr - 1 : gv + thr;
+            int cnt = 0;
             if (x >= 10 && x + 10 <= wm1 && y >= 10 && y + 10 <= hm1) {
                 // window inside the crop: six aligned words per row (the crop pitch is a multiple of 4, so the byte
                 // phase o is the same on every row), bytes compared four at a time; the per-byte "greater" flags are
-                // summed as byte counters (at most 126 per lane) and the counts are 441 minus their totals.
+                // summed as byte counters (at most 126 per lane) and the count is 441 minus their total.
                 const int a0 = (y - 10) * gp + (x - 10);
                 const int o = a0 & 3;
                 const unsigned* wp = reinterpret_cast<const unsigned*>(gray + (a0 - o));
                 const unsigned fm = 0x01010101u << (8 * o), lm = 0x01010101u >> (8 * (3 - o));      // first / last word bytes
-                const SwarPivot qa = swar_pivot(pa), qb = swar_pivot(pb);
-                unsigned ga = 0, gb = 0;
+                const SwarPivot qv = swar_pivot(pv);
+                unsigned gsum = 0;
                 const int wpitch = gp >> 2;
                 for (int dy = 0; dy < 21; ++dy) {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const unsigned W = wp[k];
                         const unsigned m = k == 0 ? fm : (k == 5 ? lm : 0x01010101u);
-                        ga += swar_gt(W, qa) & m;
-                        gb += swar_gt(W, qb) & m;
+                        gsum += swar_gt(W, qv) & m;
                     }
                     wp += wpitch;
                 }
-                const unsigned sa = (ga & 0x00ff00ffu) + ((ga >> 8) & 0x00ff00ffu), sb = (gb & 0x00ff00ffu) + ((gb >> 8) & 0x00ff00ffu);
-                ca = 441 - (int)((sa & 0xffffu) + (sa >> 16));         // (the four lanes can add up to 441: no byte-wide total)
-                cb = 441 - (int)((sb & 0xffffu) + (sb >> 16));
+                const unsigned sa = (gsum & 0x00ff00ffu) + ((gsum >> 8) & 0x00ff00ffu);
+                cnt = 441 - (int)((sa & 0xffffu) + (sa >> 16));        // (the four lanes can add up to 441: no byte-wide total)
             } else {
                 // window clipped to the crop; the replicated border rows / columns enter as weights of the edge ones
                 const int xa = max(x - 10, 0), xb = min(x + 10, wm1), ya = max(y - 10, 0), yb = min(y + 10, hm1);
@@ -537,13 +546,13 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
                 for (int r = ya; r <= yb; ++r) {
                     const uint8_t* row = gray + r * gp;
                     const int e0 = row[0], e1 = row[wm1];
-                    int ra = nl * (e0 <= pa) + nr * (e1 <= pa), rb = nl * (e0 <= pb) + nr * (e1 <= pb);
-                    for (int c = xa; c <= xb; ++c) { const int v = row[c]; ra += v <= pa; rb += v <= pb; }
+                    int ra = nl * (e0 <= pv) + nr * (e1 <= pv);
+                    for (int c = xa; c <= xb; ++c) ra += (int)row[c] <= pv;
                     const int wr = 1 + (r == 0 ? mt : 0) + (r == hm1 ? mb : 0);
-                    ca += wr * ra; cb += wr * rb;
+                    cnt += wr * ra;
                 }
             }
-            if (ca <= 220 || cb >= 221) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+            if (tb ? cnt >= 221 : cnt <= 220) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
         }
     } else
     {
@@ -561,10 +570,11 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
         const bool tail = lane + 32 * 13 < 441;                         // the 14th position exists for lanes 0..24
         for (int k2 = warp; k2 < ne; k2 += kWarps) {
             const unsigned ent = w.exact[k2];
-            const int y = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+            const int y = (int)(ent >> 16), x = (int)(ent & 0x7fffu);
+            const bool tb = (ent >> 15) & 1u;                        // which test (see rank_dirty_cell)
             const int gv = gray[y * gp + x];
-            const int pa = gv + thr, pb = gv - thr - 1;
-            unsigned ca = 0, cb = 0;
+            const int pv = tb ? gv - thr - 1 : gv + thr;
+            unsigned cnt = 0;
             if (x >= 10 && x + 10 <= wm1 && y >= 10 && y + 10 <= hm1) {  // the window lies inside the crop (uniform over the warp)
                 const uint8_t* corner = gray + (y - 10) * gp + (x - 10);
                 int vals[14];
@@ -572,19 +582,18 @@ VI_PHASE int rank_finish(const uint8_t* gray, const Geom& g, RankWs w, const int
                 for (int k = 0; k < 13; ++k) vals[k] = corner[off[k]];
                 vals[13] = tail ? (int)corner[off[13]] : 256;
 #pragma unroll
-                for (int k = 0; k < 14; ++k) { ca += vals[k] <= pa; cb += vals[k] <= pb; }
+                for (int k = 0; k < 14; ++k) cnt += vals[k] <= pv;
             } else {
 #pragma unroll
                 for (int k = 0; k < 14; ++k) {
                     const int dy = dyx[k] >> 8, dx = dyx[k] & 255;
                     const int yy = min(max(y + dy - 10, 0), hm1), xx = min(max(x + dx - 10, 0), wm1);
                     const int v = (k < 13 || tail) ? (int)gray[yy * gp + xx] : 256;
-                    ca += v <= pa; cb += v <= pb;
+                    cnt += v <= pv;
                 }
             }
-            ca = __reduce_add_sync(kFull, ca);
-            cb = __reduce_add_sync(kFull, cb);
-            if (lane == 0 && (ca <= 220 || cb >= 221)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
+            cnt = __reduce_add_sync(kFull, cnt);
+            if (lane == 0 && (tb ? cnt >= 221 : cnt <= 220)) atomicOr(&CAND[y * g.wpr + (x >> 5)], 1u << (x & 31));
         }
     }
     cta_sync();
