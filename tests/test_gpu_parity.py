@@ -197,7 +197,7 @@ def test_detect_defects(insp, cfg):
     g = rng.integers(0, 256, size=(96, 96), dtype=np.uint8)
     cases.append((g, np.full((96, 96), 255, np.uint8)))                    # uniform noise: every pixel needs the exact rank count
     g2 = crops(1, seed0=610, shape=(60, 340))[0]
-    cases.append((g2, np.full(g2.shape, 255, np.uint8)))                   # wider than the fast rank-count pass
+    cases.append((g2, np.full(g2.shape, 255, np.uint8)))                   # wide and short: several 32-cell chunks, one row segment
     g3 = rng.integers(0, 256, size=(12, 15), dtype=np.uint8)
     cases.append((g3, np.full(g3.shape, 255, np.uint8)))                   # smaller than the median window
     p = vi_b200.default_params(threshold=thr, min_area=mn, erode_px=r)
@@ -682,8 +682,8 @@ def test_ragged_grid_and_unaligned_frames(insp):
     import torch
     boxes = [((7, 5, 316, 315), 0), ((340, 9, 200, 150), 1), ((560, 20, 96, 96), 2), ((700, 3, 40, 33), 3),
              ((760, 50, 13, 21), 4), ((340, 170, 333, 120), 5), ((800, 100, 150, 230), 6), ((690, 60, 3, 3), 7),
-             ((10, 335, 500, 60), 8),        # wider than the lattice pass covers: exact rank counts for every ROI pixel
-             ((520, 340, 400, 52), 9)]       # the 15-columns-per-lane instantiation of the prefix pass
+             ((10, 335, 500, 60), 8),        # wide units: the lattice's column pass takes several 32-cell chunks per row segment,
+             ((520, 340, 400, 52), 9)]       # more tasks than warps (the Otsu warp takes columns too)
     W, H = 1001, 400
     frames = np.stack([synth.make_frame(s, [b for b, _ in boxes], H=H, W=W, inset=6, jitter=2) for s in (11, 12)])
     excl = [{'shape': 'rect', 'x': 20, 'y': 10, 'w': 30, 'h': 12}, {'shape': 'circle', 'cx': 60, 'cy': 50, 'r': 9}]
